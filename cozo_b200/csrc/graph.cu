@@ -1,0 +1,710 @@
+// graph.cu — FixedRule graph algorithms on an HBM-resident CSR:
+//   PageRank              (fixed_rule/algos/pagerank.rs:29-56 -> graph::page_rank)
+//   multi-source Dijkstra (fixed_rule/algos/shortest_path_dijkstra.rs:274-339)
+//   ClosenessCentrality   (fixed_rule/algos/all_pairs_shortest_path.rs:97-143)
+//   BetweennessCentrality (fixed_rule/algos/all_pairs_shortest_path.rs:29-95)
+// The CSR is what GraphBuilder::csr_layout(Sorted) produces for the edge stream
+// of as_directed_graph / as_directed_weighted_graph (fixed_rule/mod.rs:136-328).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+struct cozo_gpu_graph {
+  uint32_t n = 0;
+  uint64_t m = 0;
+  bool weighted = false;
+  uint32_t *out_ptr = nullptr, *out_idx = nullptr, *in_ptr = nullptr, *in_idx = nullptr;
+  float* out_w = nullptr;
+  uint32_t* hubs = nullptr;  // rows with in-degree > HUB_T
+  uint32_t n_hubs = 0;
+};
+
+namespace cozo {
+
+constexpr uint32_t HUB_T = 2048;
+
+__global__ void edge_check_kernel(const uint32_t* src, const uint32_t* dst, const float* w, uint64_t m, uint32_t n,
+                                  int* bad) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  if (src[e] >= n || dst[e] >= n) *bad = 1;
+  if (w) {
+    float x = w[e];
+    if (!(x >= 0.f) || isinf(x)) *bad = 2;  // finite and non-negative (fixed_rule/mod.rs:258-286)
+  }
+}
+
+__global__ void make_keys_kernel(const uint32_t* hi, const uint32_t* lo, uint64_t m, unsigned long long* keys,
+                                 uint32_t* deg) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  keys[e] = ((unsigned long long)hi[e] << 32) | lo[e];
+  atomicAdd(&deg[hi[e]], 1u);
+}
+
+__global__ void split_keys_kernel(const unsigned long long* keys, uint64_t m, uint32_t* lo) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  lo[e] = (uint32_t)(keys[e] & 0xFFFFFFFFull);
+}
+
+__global__ void gather_w_kernel(const float* w, const uint32_t* perm, uint64_t m, float* out) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  out[e] = w[perm[e]];
+}
+
+__global__ void iota_kernel(uint32_t* p, uint64_t m) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < m) p[e] = (uint32_t)e;
+}
+
+__global__ void find_hubs_kernel(const uint32_t* in_ptr, uint32_t n, uint32_t* hubs, uint32_t* n_hubs) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  if (in_ptr[u + 1] - in_ptr[u] > HUB_T) hubs[atomicAdd(n_hubs, 1u)] = u;
+}
+
+// ---- PageRank ----------------------------------------------------------------
+// GAP-style pull iteration (graph 0.3.1 page_rank, un-vendored):
+//   new[u] = base + d * sum_{v in in(u)} contrib[v];  err += |new[u]-old[u]| (f64)
+//   contrib'[u] = new[u] / out_degree(u)
+// 8 lanes per destination row; rows longer than HUB_T go to the hub kernel.
+__global__ void pr_init_kernel(const uint32_t* out_ptr, uint32_t n, float init, float* scores, float* contrib) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  scores[u] = init;
+  uint32_t od = out_ptr[u + 1] - out_ptr[u];
+  contrib[u] = od ? init / (float)od : 0.f;  // od==0: value is never read (no out edge leads anywhere)
+}
+
+__device__ __forceinline__ void block_add_err(double e, double* out) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if (lane == 0) sh[warp] = e;
+  __syncthreads();
+  if (warp == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    double v = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v != 0.0) atomicAdd(out, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict__ in_ptr,
+                                                      const uint32_t* __restrict__ in_idx,
+                                                      const uint32_t* __restrict__ out_ptr, uint32_t n, float base,
+                                                      float damping, const float* __restrict__ contrib_old,
+                                                      float* __restrict__ contrib_new, float* __restrict__ scores,
+                                                      double* err) {
+  const uint32_t sub = threadIdx.x & 7;
+  const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const uint32_t ngroups = (gridDim.x * blockDim.x) >> 3;
+  double e = 0.0;
+  for (uint32_t u0 = group; u0 < ((n + 3) & ~3u); u0 += ngroups) {  // keep all 32 lanes in the shuffles
+    const bool live = u0 < n;
+    uint32_t b = 0, en = 0;
+    if (live) {
+      b = in_ptr[u0];
+      en = in_ptr[u0 + 1];
+    }
+    const bool hub = en - b > HUB_T;
+    float s = 0.f;
+    if (!hub)
+      for (uint32_t k = b + sub; k < en; k += 8) s += contrib_old[in_idx[k]];
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (live && !hub && sub == 0) {
+      float nw = base + damping * s;
+      e += (double)fabsf(nw - scores[u0]);
+      scores[u0] = nw;
+      uint32_t od = out_ptr[u0 + 1] - out_ptr[u0];
+      contrib_new[u0] = od ? nw / (float)od : 0.f;
+    }
+  }
+  block_add_err(e, err);
+}
+
+__global__ void __launch_bounds__(256) pr_hub_kernel(const uint32_t* __restrict__ hubs,
+                                                     const uint32_t* __restrict__ in_ptr,
+                                                     const uint32_t* __restrict__ in_idx,
+                                                     const uint32_t* __restrict__ out_ptr, float base, float damping,
+                                                     const float* __restrict__ contrib_old,
+                                                     float* __restrict__ contrib_new, float* __restrict__ scores,
+                                                     double* err) {
+  __shared__ float sh[32];
+  const uint32_t u = hubs[blockIdx.x];
+  const uint32_t b = in_ptr[u], en = in_ptr[u + 1];
+  float s = 0.f;
+  for (uint32_t k = b + threadIdx.x; k < en; k += blockDim.x) s += contrib_old[in_idx[k]];
+  s = warp_sum(s);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) {
+      float nw = base + damping * v;
+      double e = (double)fabsf(nw - scores[u]);
+      scores[u] = nw;
+      uint32_t od = out_ptr[u + 1] - out_ptr[u];
+      contrib_new[u] = od ? nw / (float)od : 0.f;
+      if (e != 0.0) atomicAdd(err, e);
+    }
+  }
+}
+
+// ---- SSSP ---------------------------------------------------------------------
+// One CTA per source.  Label-correcting relaxation to the fixed point
+// dist[v] = min_u fl32(dist[u] + w(u,v)); with non-negative weights this is the
+// value Dijkstra's `cost + path_weight` recursion produces
+// (shortest_path_dijkstra.rs:304-309), bit for bit.  State per (source, node)
+// is one u64 = (f32 bits of dist << 32) | predecessor, updated by CAS only on a
+// strictly smaller distance (strict `<`, shortest_path_dijkstra.rs:305), so the
+// predecessors always form a tree.
+constexpr unsigned long long SSSP_INF = 0x7F800000FFFFFFFFull;  // (+inf, NONE)
+
+__global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ out_ptr,
+                                                   const uint32_t* __restrict__ out_idx,
+                                                   const float* __restrict__ out_w, uint32_t n,
+                                                   const uint32_t* __restrict__ sources, uint32_t n_src,
+                                                   unsigned long long* state, uint32_t* flags) {
+  const uint32_t si = blockIdx.x;
+  if (si >= n_src) return;
+  unsigned long long* st = state + (size_t)si * n;
+  uint32_t* cur = flags + (size_t)si * 2 * n;
+  uint32_t* nxt = cur + n;
+  __shared__ int s_any;
+  for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
+    st[v] = SSSP_INF;
+    cur[v] = 0;
+    nxt[v] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = sources[si];
+    st[s] = 0x00000000FFFFFFFFull;  // dist 0, no predecessor
+    cur[s] = 1;
+  }
+  __syncthreads();
+  for (;;) {
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    for (uint32_t u = threadIdx.x; u < n; u += blockDim.x) {
+      if (!cur[u]) continue;
+      cur[u] = 0;
+      const float du = __uint_as_float((uint32_t)(st[u] >> 32));
+      for (uint32_t k = out_ptr[u]; k < out_ptr[u + 1]; ++k) {
+        const uint32_t v = out_idx[k];
+        const float nd = du + (out_w ? out_w[k] : 1.0f);
+        unsigned long long old = st[v];
+        while (nd < __uint_as_float((uint32_t)(old >> 32))) {
+          unsigned long long want = ((unsigned long long)__float_as_uint(nd) << 32) | u;
+          unsigned long long got = atomicCAS(&st[v], old, want);
+          if (got == old) {
+            nxt[v] = 1;
+            s_any = 1;
+            break;
+          }
+          old = got;
+        }
+      }
+    }
+    __syncthreads();
+    const int any = s_any;
+    __syncthreads();
+    if (!any) break;
+    uint32_t* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+}
+
+__global__ void sssp_unpack_kernel(const unsigned long long* state, uint64_t total, float* dist, uint32_t* pred) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  unsigned long long s = state[i];
+  if (dist) dist[i] = __uint_as_float((uint32_t)(s >> 32));
+  if (pred) pred[i] = (uint32_t)(s & 0xFFFFFFFFull);
+}
+
+// closeness of one source: nc^2 / total / (n-1), nc counting the source itself
+// (all_pairs_shortest_path.rs:118-120)
+__global__ void __launch_bounds__(256) closeness_kernel(const unsigned long long* state, uint32_t n, uint32_t n_src,
+                                                        uint32_t src_base, float* out) {
+  const uint32_t si = blockIdx.x;
+  if (si >= n_src) return;
+  const unsigned long long* st = state + (size_t)si * n;
+  double tot = 0.0;
+  uint32_t cnt = 0;
+  for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
+    float d = __uint_as_float((uint32_t)(st[v] >> 32));
+    if (isfinite(d)) {
+      tot += (double)d;
+      cnt++;
+    }
+  }
+  __shared__ double sh_t[8];
+  __shared__ uint32_t sh_c[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    sh_t[warp] = tot;
+    sh_c[warp] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    uint32_t c = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      t += sh_t[i];
+      c += sh_c[i];
+    }
+    float nc = (float)c;
+    float total = (float)t;
+    out[src_base + si] = nc * nc / total / (float)(n - 1);
+  }
+}
+
+// Betweenness of one source (Brandes form of all_pairs_shortest_path.rs:54-68:
+// every tied shortest path adds 1/l to each interior node, i.e. node v receives
+// sigma_st(v)/sigma_st per target t).  sigma and delta are iterated to their
+// fixed points over the shortest-path DAG { (u,v) : fl32(dist[u]+w) == dist[v] }.
+__global__ void __launch_bounds__(256) betweenness_kernel(const uint32_t* __restrict__ out_ptr,
+                                                          const uint32_t* __restrict__ out_idx,
+                                                          const float* __restrict__ out_w, uint32_t n,
+                                                          const uint32_t* __restrict__ sources, uint32_t n_src,
+                                                          const unsigned long long* state, double* sigma_buf,
+                                                          double* delta_buf, double* bc) {
+  const uint32_t si = blockIdx.x;
+  if (si >= n_src) return;
+  const unsigned long long* st = state + (size_t)si * n;
+  double* sigma = sigma_buf + (size_t)si * 2 * n;
+  double* sigma2 = sigma + n;
+  double* delta = delta_buf + (size_t)si * 2 * n;
+  double* delta2 = delta + n;
+  const uint32_t s = sources[si];
+  __shared__ int s_any;
+  for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
+    sigma[v] = v == s ? 1.0 : 0.0;
+    sigma2[v] = 0.0;
+    delta[v] = 0.0;
+    delta2[v] = 0.0;
+  }
+  __syncthreads();
+  // sigma: push along DAG edges until nothing changes (<= DAG depth rounds)
+  for (uint32_t round = 0; round < n + 1; ++round) {
+    if (threadIdx.x == 0) s_any = 0;
+    for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) sigma2[v] = v == s ? 1.0 : 0.0;
+    __syncthreads();
+    for (uint32_t u = threadIdx.x; u < n; u += blockDim.x) {
+      const float du = __uint_as_float((uint32_t)(st[u] >> 32));
+      if (!isfinite(du) || sigma[u] == 0.0) continue;
+      for (uint32_t k = out_ptr[u]; k < out_ptr[u + 1]; ++k) {
+        const uint32_t v = out_idx[k];
+        if (v == s) continue;
+        const float dv = __uint_as_float((uint32_t)(st[v] >> 32));
+        if (du + (out_w ? out_w[k] : 1.0f) == dv) atomicAdd(&sigma2[v], sigma[u]);
+      }
+    }
+    __syncthreads();
+    for (uint32_t v = threadIdx.x; v < n; v += blockDim.x)
+      if (sigma2[v] != sigma[v]) s_any = 1;
+    __syncthreads();
+    const int any = s_any;
+    double* t = sigma;
+    sigma = sigma2;
+    sigma2 = t;
+    __syncthreads();
+    if (!any) break;
+  }
+  // delta: pull from DAG successors until nothing changes
+  for (uint32_t round = 0; round < n + 1; ++round) {
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    for (uint32_t u = threadIdx.x; u < n; u += blockDim.x) {
+      const float du = __uint_as_float((uint32_t)(st[u] >> 32));
+      double acc = 0.0;
+      if (isfinite(du) && sigma[u] != 0.0) {
+        for (uint32_t k = out_ptr[u]; k < out_ptr[u + 1]; ++k) {
+          const uint32_t v = out_idx[k];
+          if (v == s) continue;
+          const float dv = __uint_as_float((uint32_t)(st[v] >> 32));
+          if (du + (out_w ? out_w[k] : 1.0f) == dv) acc += sigma[u] / sigma[v] * (1.0 + delta[v]);
+        }
+      }
+      delta2[u] = acc;
+      if (acc != delta[u]) s_any = 1;
+    }
+    __syncthreads();
+    const int any = s_any;
+    double* t = delta;
+    delta = delta2;
+    delta2 = t;
+    __syncthreads();
+    if (!any) break;
+  }
+  for (uint32_t v = threadIdx.x; v < n; v += blockDim.x)
+    if (v != s && delta[v] != 0.0) atomicAdd(&bc[v], delta[v]);
+}
+
+__global__ void f64_to_f32_kernel(const double* in, uint32_t n, float* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+static bool poisoned(const volatile int* p) { return p && *p != 0; }
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  template <class T>
+  T* as() {
+    return static_cast<T*>(p);
+  }
+};
+
+}  // namespace cozo
+
+using namespace cozo;
+
+extern "C" void cozo_gpu_graph_free(cozo_gpu_graph_t* g) {
+  if (!g) return;
+  void* ptrs[] = {g->out_ptr, g->out_idx, g->in_ptr, g->in_idx, g->out_w, g->hubs};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete g;
+}
+
+extern "C" int cozo_gpu_graph_stage(cozo_gpu_graph_t** out, uint32_t n, uint64_t m, const uint32_t* src,
+                                    const uint32_t* dst, const float* w) {
+  if (!out) return set_error(COZO_GPU_EINVAL, "null argument");
+  *out = nullptr;
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (m && (!src || !dst)) return set_error(COZO_GPU_EINVAL, "null edge arrays");
+  if (m >= 0xFFFFFFFFull) return set_error(COZO_GPU_EUNSUP, "more than 2^32-2 edges");
+  auto* g = new cozo_gpu_graph();
+  g->n = n;
+  g->m = m;
+  g->weighted = w != nullptr;
+  auto fail = [&](int code) {
+    cozo_gpu_graph_free(g);
+    return code;
+  };
+#define G_CUDA(call)                                                                              \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(set_error(_e == cudaErrorMemoryAllocation ? COZO_GPU_ENOMEM : COZO_GPU_ECUDA,    \
+                            "%s failed: %s (line %d)", #call, cudaGetErrorString(_e), __LINE__)); \
+  } while (0)
+  const size_t np1 = (size_t)n + 1;
+  const size_t mm = std::max<uint64_t>(m, 1);
+  G_CUDA(cudaMalloc(&g->out_ptr, np1 * 4));
+  G_CUDA(cudaMalloc(&g->in_ptr, np1 * 4));
+  G_CUDA(cudaMalloc(&g->out_idx, mm * 4));
+  G_CUDA(cudaMalloc(&g->in_idx, mm * 4));
+  if (w) G_CUDA(cudaMalloc(&g->out_w, mm * 4));
+  G_CUDA(cudaMemset(g->out_ptr, 0, np1 * 4));
+  G_CUDA(cudaMemset(g->in_ptr, 0, np1 * 4));
+  if (m) {
+    DevBuf dsrc, ddst, dw, keys, keys2, perm, perm2, tmp, bad;
+    G_CUDA(cudaMalloc(&dsrc.p, m * 4));
+    G_CUDA(cudaMalloc(&ddst.p, m * 4));
+    G_CUDA(cudaMalloc(&keys.p, m * 8));
+    G_CUDA(cudaMalloc(&keys2.p, m * 8));
+    G_CUDA(cudaMalloc(&bad.p, 4));
+    G_CUDA(cudaMemset(bad.p, 0, 4));
+    G_CUDA(cudaMemcpy(dsrc.p, src, m * 4, cudaMemcpyHostToDevice));
+    G_CUDA(cudaMemcpy(ddst.p, dst, m * 4, cudaMemcpyHostToDevice));
+    if (w) {
+      G_CUDA(cudaMalloc(&dw.p, m * 4));
+      G_CUDA(cudaMemcpy(dw.p, w, m * 4, cudaMemcpyHostToDevice));
+    }
+    const uint32_t tb = 256;
+    const uint32_t gb = (uint32_t)((m + tb - 1) / tb);
+    edge_check_kernel<<<gb, tb>>>(dsrc.as<uint32_t>(), ddst.as<uint32_t>(), dw.as<float>(), m, n, bad.as<int>());
+    int hbad = 0;
+    G_CUDA(cudaMemcpy(&hbad, bad.p, 4, cudaMemcpyDeviceToHost));
+    if (hbad == 1) return fail(set_error(COZO_GPU_EINVAL, "edge endpoint out of range (n=%u)", n));
+    if (hbad == 2) return fail(set_error(COZO_GPU_EINVAL, "edge weight must be finite and non-negative"));
+    int end_bit = 32;
+    while (end_bit < 64 && (n >> (end_bit - 32)) != 0) ++end_bit;  // bits of the row id
+    size_t tmp_bytes = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.as<unsigned long long>(), keys2.as<unsigned long long>(),
+                                    (uint32_t*)nullptr, (uint32_t*)nullptr, (int)m, 0, end_bit);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, g->out_ptr, g->out_ptr, (int)np1);
+    tmp_bytes = std::max(tmp_bytes, tb2);
+    G_CUDA(cudaMalloc(&tmp.p, tmp_bytes));
+    // out-CSR: sort by (src, dst); equal pairs keep input order (stable LSD radix sort)
+    make_keys_kernel<<<gb, tb>>>(dsrc.as<uint32_t>(), ddst.as<uint32_t>(), m, keys.as<unsigned long long>(),
+                                 g->out_ptr);
+    if (w) {
+      G_CUDA(cudaMalloc(&perm.p, m * 4));
+      G_CUDA(cudaMalloc(&perm2.p, m * 4));
+      iota_kernel<<<gb, tb>>>(perm.as<uint32_t>(), m);
+      size_t t3 = tmp_bytes;
+      cub::DeviceRadixSort::SortPairs(tmp.p, t3, keys.as<unsigned long long>(), keys2.as<unsigned long long>(),
+                                      perm.as<uint32_t>(), perm2.as<uint32_t>(), (int)m, 0, end_bit);
+      gather_w_kernel<<<gb, tb>>>(dw.as<float>(), perm2.as<uint32_t>(), m, g->out_w);
+    } else {
+      size_t t3 = tmp_bytes;
+      cub::DeviceRadixSort::SortKeys(tmp.p, t3, keys.as<unsigned long long>(), keys2.as<unsigned long long>(), (int)m,
+                                     0, end_bit);
+    }
+    split_keys_kernel<<<gb, tb>>>(keys2.as<unsigned long long>(), m, g->out_idx);
+    {
+      size_t t3 = tmp_bytes;
+      cub::DeviceScan::ExclusiveSum(tmp.p, t3, g->out_ptr, g->out_ptr, (int)np1);
+    }
+    // in-CSR: sort by (dst, src)
+    make_keys_kernel<<<gb, tb>>>(ddst.as<uint32_t>(), dsrc.as<uint32_t>(), m, keys.as<unsigned long long>(),
+                                 g->in_ptr);
+    {
+      size_t t3 = tmp_bytes;
+      cub::DeviceRadixSort::SortKeys(tmp.p, t3, keys.as<unsigned long long>(), keys2.as<unsigned long long>(), (int)m,
+                                     0, end_bit);
+    }
+    split_keys_kernel<<<gb, tb>>>(keys2.as<unsigned long long>(), m, g->in_idx);
+    {
+      size_t t3 = tmp_bytes;
+      cub::DeviceScan::ExclusiveSum(tmp.p, t3, g->in_ptr, g->in_ptr, (int)np1);
+    }
+    G_CUDA(cudaGetLastError());
+    G_CUDA(cudaDeviceSynchronize());
+  }
+  if (n) {
+    DevBuf cnt;
+    G_CUDA(cudaMalloc(&g->hubs, (size_t)n * 4));
+    G_CUDA(cudaMalloc(&cnt.p, 4));
+    G_CUDA(cudaMemset(cnt.p, 0, 4));
+    find_hubs_kernel<<<(n + 255) / 256, 256>>>(g->in_ptr, n, g->hubs, cnt.as<uint32_t>());
+    G_CUDA(cudaMemcpy(&g->n_hubs, cnt.p, 4, cudaMemcpyDeviceToHost));
+  }
+#undef G_CUDA
+  *out = g;
+  return 0;
+}
+
+extern "C" int cozo_gpu_graph_export(cozo_gpu_graph_t* g, uint32_t* out_ptr, uint32_t* out_idx, float* out_w,
+                                     uint32_t* in_ptr, uint32_t* in_idx) {
+  if (!g) return set_error(COZO_GPU_EINVAL, "null graph handle");
+  const size_t np1 = (size_t)g->n + 1;
+  if (out_ptr) COZO_CUDA(cudaMemcpy(out_ptr, g->out_ptr, np1 * 4, cudaMemcpyDeviceToHost));
+  if (in_ptr) COZO_CUDA(cudaMemcpy(in_ptr, g->in_ptr, np1 * 4, cudaMemcpyDeviceToHost));
+  if (out_idx && g->m) COZO_CUDA(cudaMemcpy(out_idx, g->out_idx, g->m * 4, cudaMemcpyDeviceToHost));
+  if (in_idx && g->m) COZO_CUDA(cudaMemcpy(in_idx, g->in_idx, g->m * 4, cudaMemcpyDeviceToHost));
+  if (out_w && g->m && g->out_w) COZO_CUDA(cudaMemcpy(out_w, g->out_w, g->m * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol, uint32_t max_iter,
+                                 float* out_scores, uint32_t* out_iters, double* out_err, double* out_kernel_ms,
+                                 const volatile int* poison) {
+  if (!g || !out_scores) return set_error(COZO_GPU_EINVAL, "null argument");
+  if (max_iter == 0) return set_error(COZO_GPU_EINVAL, "iterations must be positive");  // pos_integer_option
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (out_iters) *out_iters = 0;
+  if (out_err) *out_err = 0;
+  if (out_kernel_ms) *out_kernel_ms = 0;
+  const uint32_t n = g->n;
+  if (n == 0) return 0;  // pagerank.rs:43-45
+  const DeviceInfo& di = device_info();
+  DevBuf scores, c0, c1, err;
+  COZO_CUDA(cudaMalloc(&scores.p, (size_t)n * 4));
+  COZO_CUDA(cudaMalloc(&c0.p, (size_t)n * 4));
+  COZO_CUDA(cudaMalloc(&c1.p, (size_t)n * 4));
+  COZO_CUDA(cudaMalloc(&err.p, 8));
+  cudaEvent_t e0, e1;
+  COZO_CUDA(cudaEventCreate(&e0));
+  COZO_CUDA(cudaEventCreate(&e1));
+  const float init = 1.0f / (float)n;
+  const float base = (1.0f - damping) / (float)n;
+  COZO_CUDA(cudaEventRecord(e0));
+  pr_init_kernel<<<(n + 255) / 256, 256>>>(g->out_ptr, n, init, scores.as<float>(), c0.as<float>());
+  float* cold = c0.as<float>();
+  float* cnew = c1.as<float>();
+  uint32_t iter = 0;
+  double herr = 0;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)di.sm_count * 8 * 4);
+  int ret = 0;
+  for (;;) {
+    if (poisoned(poison)) {
+      ret = set_error(COZO_GPU_EKILLED, "Running query is killed before completion");
+      break;
+    }
+    cudaMemsetAsync(err.p, 0, 8);
+    pr_iter_kernel<<<grid, 256>>>(g->in_ptr, g->in_idx, g->out_ptr, n, base, damping, cold, cnew, scores.as<float>(),
+                                  err.as<double>());
+    if (g->n_hubs)
+      pr_hub_kernel<<<g->n_hubs, 256>>>(g->hubs, g->in_ptr, g->in_idx, g->out_ptr, base, damping, cold, cnew,
+                                        scores.as<float>(), err.as<double>());
+    cudaError_t ce = cudaMemcpy(&herr, err.p, 8, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) {
+      ret = set_error(COZO_GPU_ECUDA, "pagerank iteration failed: %s", cudaGetErrorString(ce));
+      break;
+    }
+    std::swap(cold, cnew);
+    ++iter;
+    if (herr < tol || iter == max_iter) break;
+  }
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ret) return ret;
+  COZO_CUDA(cudaMemcpy(out_scores, scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (out_iters) *out_iters = iter;
+  if (out_err) *out_err = herr;
+  if (out_kernel_ms) *out_kernel_ms = ms;
+  return 0;
+}
+
+namespace cozo {
+// shared driver of the SSSP family: runs sources in chunks that fit `budget` bytes
+template <class PerChunk>
+static int sssp_chunks(cozo_gpu_graph_t* g, const uint32_t* sources_host, uint32_t n_src, size_t extra_per_src,
+                       const volatile int* poison, double* out_ms, PerChunk per_chunk) {
+  const uint32_t n = g->n;
+  const size_t per_src = (size_t)n * (8 + 8) + extra_per_src;
+  size_t freeb = 0, totalb = 0;
+  COZO_CUDA(cudaMemGetInfo(&freeb, &totalb));
+  size_t budget = std::min<size_t>(freeb / 2, (size_t)8 << 30);
+  uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_src, budget / std::max<size_t>(per_src, 1)));
+  DevBuf state, flags, dsrc;
+  COZO_CUDA(cudaMalloc(&state.p, (size_t)chunk * n * 8));
+  COZO_CUDA(cudaMalloc(&flags.p, (size_t)chunk * n * 8));
+  COZO_CUDA(cudaMalloc(&dsrc.p, (size_t)chunk * 4));
+  cudaEvent_t e0, e1;
+  COZO_CUDA(cudaEventCreate(&e0));
+  COZO_CUDA(cudaEventCreate(&e1));
+  COZO_CUDA(cudaEventRecord(e0));
+  int ret = 0;
+  for (uint32_t s0 = 0; s0 < n_src && !ret; s0 += chunk) {
+    if (poisoned(poison)) {
+      ret = set_error(COZO_GPU_EKILLED, "Running query is killed before completion");
+      break;
+    }
+    uint32_t c = std::min(chunk, n_src - s0);
+    cudaMemcpy(dsrc.p, sources_host + s0, (size_t)c * 4, cudaMemcpyHostToDevice);
+    sssp_kernel<<<c, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc.as<uint32_t>(), c,
+                            state.as<unsigned long long>(), flags.as<uint32_t>());
+    ret = per_chunk(s0, c, state.as<unsigned long long>(), dsrc.as<uint32_t>());
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (!ret && ce != cudaSuccess) ret = set_error(COZO_GPU_ECUDA, "sssp failed: %s", cudaGetErrorString(ce));
+  }
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (out_ms) *out_ms = ms;
+  return ret;
+}
+}  // namespace cozo
+
+extern "C" int cozo_gpu_sssp_multi(cozo_gpu_graph_t* g, const uint32_t* sources, uint32_t n_src, float* out_dist,
+                                   uint32_t* out_pred, double* out_kernel_ms, const volatile int* poison) {
+  if (!g || (n_src && (!sources || !out_dist))) return set_error(COZO_GPU_EINVAL, "null argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (out_kernel_ms) *out_kernel_ms = 0;
+  const uint32_t n = g->n;
+  if (n_src == 0 || n == 0) return 0;
+  for (uint32_t i = 0; i < n_src; ++i)
+    if (sources[i] >= n) return set_error(COZO_GPU_EINVAL, "source %u out of range", sources[i]);
+  DevBuf dd, dp;
+  return sssp_chunks(g, sources, n_src, (size_t)n * 8, poison, out_kernel_ms,
+                     [&](uint32_t s0, uint32_t c, unsigned long long* state, uint32_t*) -> int {
+                       const uint64_t total = (uint64_t)c * n;
+                       if (!dd.p) {
+                         COZO_CUDA(cudaMalloc(&dd.p, total * 4));
+                         COZO_CUDA(cudaMalloc(&dp.p, total * 4));
+                       }
+                       sssp_unpack_kernel<<<(uint32_t)((total + 255) / 256), 256>>>(state, total, dd.as<float>(),
+                                                                                    dp.as<uint32_t>());
+                       COZO_CUDA(cudaMemcpy(out_dist + (size_t)s0 * n, dd.p, total * 4, cudaMemcpyDeviceToHost));
+                       if (out_pred)
+                         COZO_CUDA(cudaMemcpy(out_pred + (size_t)s0 * n, dp.p, total * 4, cudaMemcpyDeviceToHost));
+                       return 0;
+                     });
+}
+
+extern "C" int cozo_gpu_closeness(cozo_gpu_graph_t* g, float* out, double* out_kernel_ms,
+                                  const volatile int* poison) {
+  if (!g || !out) return set_error(COZO_GPU_EINVAL, "null argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (out_kernel_ms) *out_kernel_ms = 0;
+  const uint32_t n = g->n;
+  if (n == 0) return 0;  // all_pairs_shortest_path.rs:111-113
+  std::vector<uint32_t> sources(n);
+  for (uint32_t i = 0; i < n; ++i) sources[i] = i;
+  DevBuf dout;
+  COZO_CUDA(cudaMalloc(&dout.p, (size_t)n * 4));
+  rc = sssp_chunks(g, sources.data(), n, 0, poison, out_kernel_ms,
+                   [&](uint32_t s0, uint32_t c, unsigned long long* state, uint32_t*) -> int {
+                     closeness_kernel<<<c, 256>>>(state, n, c, s0, dout.as<float>());
+                     return 0;
+                   });
+  if (rc) return rc;
+  COZO_CUDA(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int cozo_gpu_betweenness(cozo_gpu_graph_t* g, float* out, double* out_kernel_ms,
+                                    const volatile int* poison) {
+  if (!g || !out) return set_error(COZO_GPU_EINVAL, "null argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (out_kernel_ms) *out_kernel_ms = 0;
+  const uint32_t n = g->n;
+  if (n == 0) return 0;  // all_pairs_shortest_path.rs:43-46
+  std::vector<uint32_t> sources(n);
+  for (uint32_t i = 0; i < n; ++i) sources[i] = i;
+  DevBuf bc, bcf, sig, del;
+  COZO_CUDA(cudaMalloc(&bc.p, (size_t)n * 8));
+  COZO_CUDA(cudaMemset(bc.p, 0, (size_t)n * 8));
+  COZO_CUDA(cudaMalloc(&bcf.p, (size_t)n * 4));
+  size_t sig_cap = 0;
+  rc = sssp_chunks(g, sources.data(), n, (size_t)n * 32, poison, out_kernel_ms,
+                   [&](uint32_t, uint32_t c, unsigned long long* state, uint32_t* dsrc) -> int {
+                     size_t need = (size_t)c * 2 * n * 8;
+                     if (sig_cap < need) {
+                       if (sig.p) cudaFree(sig.p);
+                       if (del.p) cudaFree(del.p);
+                       sig.p = del.p = nullptr;
+                       COZO_CUDA(cudaMalloc(&sig.p, need));
+                       COZO_CUDA(cudaMalloc(&del.p, need));
+                       sig_cap = need;
+                     }
+                     betweenness_kernel<<<c, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc, c, state,
+                                                    sig.as<double>(), del.as<double>(), bc.as<double>());
+                     return 0;
+                   });
+  if (rc) return rc;
+  f64_to_f32_kernel<<<(n + 255) / 256, 256>>>(bc.as<double>(), n, bcf.as<float>());
+  COZO_CUDA(cudaMemcpy(out, bcf.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}

@@ -1,0 +1,635 @@
+// hnsw.cu — staging, batched k-NN search and export of the HBM-resident HNSW
+// index.  Replaces SessionTx::hnsw_knn (runtime/hnsw.rs:869-1012) behind
+// HnswSearchRA::iter (query/ra.rs:1085-1121); see include/cozo_gpu.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "hnsw_host.hpp"
+
+namespace cozo {
+
+struct SearchParams {
+  const float* queries;
+  uint32_t B, k, ef;
+  int has_radius;
+  double radius;
+  uint32_t* out_ids;
+  float* out_dist;
+  uint32_t* out_count;
+  uint32_t* qstats;
+  uint32_t* counter;
+  uint32_t* vis;
+  uint32_t nwords;
+  uint32_t* vlog;
+  uint32_t logcap;
+  uint32_t ns;
+  uint32_t warp_smem;  // bytes of shared memory per warp
+  uint32_t off_fi, off_pend, off_bars, off_ring;
+};
+
+// One warp per query, persistent CTAs pulling query indices from a counter.
+template <int NV, int METRIC, bool BULK>
+__global__ void __launch_bounds__(256, 2) hnsw_search_kernel(HnswDev g, SearchParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+  uint8_t* base = smem + (size_t)warp * p.warp_smem;
+  WarpCtx w;
+  w.fd = reinterpret_cast<float*>(base);
+  w.fi = reinterpret_cast<uint32_t*>(base + p.off_fi);
+  w.pend = reinterpret_cast<uint32_t*>(base + p.off_pend);
+  w.bars = reinterpret_cast<uint64_t*>(base + p.off_bars);
+  w.ring = reinterpret_cast<float*>(base + p.off_ring);
+  const size_t slot = (size_t)blockIdx.x * wpc + warp;
+  w.vis = p.vis + slot * p.nwords;
+  w.nwords = p.nwords;
+  w.vlog = p.vlog + slot * p.logcap;
+  w.logcap = p.logcap;
+  w.ns = p.ns;
+  w.nlog = 0;
+  w.head = 0;
+  w.phase = 0;
+  if (BULK) {
+    if (lane == 0) {
+      for (uint32_t s = 0; s < p.ns; ++s) mbar_init(&w.bars[s], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+  const int nvec4 = g.ld >> 2;
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(p.counter, 1u);
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (qi >= p.B) break;
+    float4 q[NV];
+    float qnorm;
+    load_query<NV>(p.queries + (size_t)qi * g.dim, g.dim, lane, q, qnorm);
+    w.len = 0;
+    w.cursor = 0;
+    w.dist_evals = w.nodes_expanded = w.nbr_reads = 0;
+    uint32_t found = 0;
+    if (g.entry != NONE) {  // empty index => no rows (hnsw.rs:903-909)
+      // entry point distance (hnsw.rs:915-918)
+      float d = dist_ldg1<NV, METRIC>(q, reinterpret_cast<const float4*>(g.vec + (size_t)g.entry * g.ld), lane, nvec4,
+                                      qnorm);
+      w.dist_evals = 1;
+      if (lane == 0) {
+        w.fd[0] = d;
+        w.fi[0] = g.entry;
+      }
+      w.len = 1;
+      __syncwarp();
+      for (uint32_t lvl = g.top_level; lvl >= 1; --lvl)  // hnsw.rs:919-929
+        search_level<NV, METRIC, BULK>(g, w, q, qnorm, 1, lvl, lane);
+      search_level<NV, METRIC, BULK>(g, w, q, qnorm, p.ef, 0, lane);  // hnsw.rs:930-938
+      // trim to k, drop dist > radius, nearest first (hnsw.rs:943-956,1005-1006)
+      found = w.len < p.k ? w.len : p.k;
+      if (p.has_radius) {
+        uint32_t c = 0;
+        for (uint32_t base_i = 0; base_i < found; base_i += 32) {
+          uint32_t i = base_i + lane;
+          bool in = i < found && !((double)w.fd[i] > p.radius);
+          c += __popc(__ballot_sync(0xffffffffu, in));
+        }
+        found = c;
+      }
+    }
+    for (uint32_t i = lane; i < p.k; i += 32) {
+      bool in = i < found;
+      p.out_ids[(size_t)qi * p.k + i] = in ? (w.fi[i] & IDMASK) : NONE;
+      p.out_dist[(size_t)qi * p.k + i] = in ? w.fd[i] : INFINITY;
+    }
+    if (lane == 0) {
+      if (p.out_count) p.out_count[qi] = found;
+      if (p.qstats) {
+        uint4 s = make_uint4(w.dist_evals, w.nodes_expanded, w.nbr_reads, 0);
+        reinterpret_cast<uint4*>(p.qstats)[qi] = s;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+using KernelFn = void (*)(HnswDev, SearchParams);
+
+template <int NV>
+static KernelFn pick_metric(int metric, bool bulk) {
+  switch (metric) {
+    case COZO_GPU_L2:
+      return bulk ? hnsw_search_kernel<NV, COZO_GPU_L2, true> : hnsw_search_kernel<NV, COZO_GPU_L2, false>;
+    case COZO_GPU_COSINE:
+      return bulk ? hnsw_search_kernel<NV, COZO_GPU_COSINE, true> : hnsw_search_kernel<NV, COZO_GPU_COSINE, false>;
+    default:
+      return bulk ? hnsw_search_kernel<NV, COZO_GPU_IP, true> : hnsw_search_kernel<NV, COZO_GPU_IP, false>;
+  }
+}
+
+static KernelFn pick_kernel(uint32_t ld, int metric, bool bulk) {
+  uint32_t need = (ld / 4 + 31) / 32;
+  if (need <= 1) return pick_metric<1>(metric, bulk);
+  if (need <= 2) return pick_metric<2>(metric, bulk);
+  if (need <= 4) return pick_metric<4>(metric, bulk);
+  if (need <= 6) return pick_metric<6>(metric, bulk);
+  if (need <= 8) return pick_metric<8>(metric, bulk);
+  if (need <= 16) return pick_metric<16>(metric, bulk);
+  return nullptr;
+}
+
+int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words) {
+  if (ws->vis_words < vis_words) {
+    if (ws->vis) cudaFree(ws->vis);
+    ws->vis = nullptr;
+    ws->vis_words = 0;
+    COZO_CUDA(cudaMalloc(&ws->vis, vis_words * 4));
+    COZO_CUDA(cudaMemset(ws->vis, 0, vis_words * 4));
+    ws->vis_words = vis_words;
+  }
+  if (ws->vlog_words < vlog_words) {
+    if (ws->vlog) cudaFree(ws->vlog);
+    ws->vlog = nullptr;
+    ws->vlog_words = 0;
+    COZO_CUDA(cudaMalloc(&ws->vlog, vlog_words * 4));
+    ws->vlog_words = vlog_words;
+  }
+  return 0;
+}
+
+HnswWorkspace* hnsw_acquire_ws(cozo_gpu_hnsw* h) {
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->pool.empty()) {
+      HnswWorkspace* ws = h->pool.back();
+      h->pool.pop_back();
+      return ws;
+    }
+  }
+  auto* ws = new HnswWorkspace();
+  if (cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ws->e0) != cudaSuccess || cudaEventCreate(&ws->e1) != cudaSuccess ||
+      cudaMalloc(&ws->counter, 256) != cudaSuccess) {
+    set_error(COZO_GPU_ECUDA, "workspace creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete ws;
+    return nullptr;
+  }
+  return ws;
+}
+
+void hnsw_release_ws(cozo_gpu_hnsw* h, HnswWorkspace* ws) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->pool.push_back(ws);
+}
+
+static void free_ws(HnswWorkspace* ws) {
+  if (ws->vis) cudaFree(ws->vis);
+  if (ws->vlog) cudaFree(ws->vlog);
+  if (ws->counter) cudaFree(ws->counter);
+  if (ws->q) cudaFree(ws->q);
+  if (ws->ids) cudaFree(ws->ids);
+  if (ws->dist) cudaFree(ws->dist);
+  if (ws->count) cudaFree(ws->count);
+  if (ws->qstats) cudaFree(ws->qstats);
+  if (ws->e0) cudaEventDestroy(ws->e0);
+  if (ws->e1) cudaEventDestroy(ws->e1);
+  if (ws->stream) cudaStreamDestroy(ws->stream);
+  delete ws;
+}
+
+int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, uint32_t B, uint32_t k, uint32_t ef,
+                       double radius, uint32_t* d_ids, float* d_dist, uint32_t* d_count, uint32_t* d_qstats,
+                       cudaStream_t stream) {
+  const DeviceInfo& di = device_info();
+  const HnswDev& g = h->dev;
+  if (B == 0) return 0;
+  const bool bulk = get_option("hnsw.mode", 1) != 0;
+  uint32_t wpc = (uint32_t)get_option("hnsw.warps_per_cta", 4);
+  if (wpc < 1) wpc = 1;
+  if (wpc > 8) wpc = 8;
+  uint32_t ns = (uint32_t)get_option("hnsw.stages", 4);
+  if (ns < 1) ns = 1;
+  if (ns > 32) ns = 32;
+  if (!bulk) ns = 0;
+  KernelFn fn = pick_kernel(g.ld, g.metric, bulk);
+  if (!fn) return set_error(COZO_GPU_EUNSUP, "vec_dim %u exceeds the supported maximum 2048", g.dim);
+
+  SearchParams p{};
+  uint32_t efcap = round_up(ef, 32);
+  p.off_fi = efcap * 4;
+  p.off_pend = p.off_fi + efcap * 4;
+  p.off_bars = p.off_pend + 32 * 4;
+  p.off_ring = round_up(p.off_bars + ns * 8, 128);
+  p.warp_smem = round_up(p.off_ring + ns * g.ld * 4, 128);
+  size_t smem = (size_t)p.warp_smem * wpc;
+  while (smem > di.smem_optin && wpc > 1) {
+    wpc >>= 1;
+    smem = (size_t)p.warp_smem * wpc;
+  }
+  if (smem > di.smem_optin)
+    return set_error(COZO_GPU_EUNSUP, "ef=%u needs %zu B of shared memory per warp (limit %zu)", ef, smem,
+                     di.smem_optin);
+  COZO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ctas_per_sm = 0;
+  COZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, wpc * 32, smem));
+  if (ctas_per_sm < 1) return set_error(COZO_GPU_ECUDA, "search kernel does not fit on an SM");
+  int64_t cap = get_option("hnsw.max_ctas_per_sm", 0);
+  if (cap > 0 && ctas_per_sm > cap) ctas_per_sm = (int)cap;
+  uint32_t grid = (uint32_t)di.sm_count * (uint32_t)ctas_per_sm;
+  uint32_t need = (B + wpc - 1) / wpc;
+  if (grid > need) grid = need;
+
+  uint32_t nwords = round_up((g.n + 31) / 32, 4);
+  uint32_t logcap = std::min<uint32_t>(65536u, std::max<uint32_t>(4096u, 64u * ef));
+  size_t slots = (size_t)grid * wpc;
+  int rc = hnsw_ws_reserve(ws, slots * nwords, slots * logcap);
+  if (rc) return rc;
+
+  p.queries = d_q;
+  p.B = B;
+  p.k = k;
+  p.ef = ef;
+  p.has_radius = radius >= 0.0;
+  p.radius = radius;
+  p.out_ids = d_ids;
+  p.out_dist = d_dist;
+  p.out_count = d_count;
+  p.qstats = d_qstats;
+  p.counter = ws->counter;
+  p.vis = ws->vis;
+  p.nwords = nwords;
+  p.vlog = ws->vlog;
+  p.logcap = logcap;
+  p.ns = ns;
+  COZO_CUDA(cudaMemsetAsync(ws->counter, 0, 4, stream));
+  fn<<<grid, wpc * 32, smem, stream>>>(g, p);
+  COZO_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cozo
+
+using namespace cozo;
+
+// ---------------------------------------------------------------------------
+extern "C" int cozo_gpu_hnsw_stage(cozo_gpu_hnsw_t** out, const CozoGpuHnswStageDesc* d) {
+  if (!out || !d) return set_error(COZO_GPU_EINVAL, "null argument");
+  *out = nullptr;
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (d->dim == 0 || d->n_levels == 0 || !d->levels || (d->n_vectors && !d->vectors))
+    return set_error(COZO_GPU_EINVAL, "bad stage descriptor");
+  if (d->metric < 0 || d->metric > 2) return set_error(COZO_GPU_EINVAL, "unknown distance %d", d->metric);
+  if (d->n_vectors >= 0x7FFFFFFFu) return set_error(COZO_GPU_EUNSUP, "more than 2^31-1 vectors in one shard");
+  if (d->n_levels > 200) return set_error(COZO_GPU_EINVAL, "too many layers");
+  const uint32_t n = d->n_vectors;
+  if (d->levels[0].n_nodes != n) return set_error(COZO_GPU_EINVAL, "layer 0 must cover all %u vectors", n);
+  if (d->entry_point != COZO_GPU_NONE && d->entry_point >= n)
+    return set_error(COZO_GPU_EINVAL, "entry point out of range");
+
+  auto* h = new cozo_gpu_hnsw();
+  h->n_levels = d->n_levels;
+  h->m_max0 = d->m_max0;
+  h->m_max = d->m_max;
+  HnswDev& g = h->dev;
+  g.n = n;
+  g.dim = d->dim;
+  g.ld = round_up(d->dim, 4);
+  g.metric = d->metric;
+  g.entry = d->entry_point;
+  g.top_level = d->n_levels - 1;
+
+  // strides: observed max degree, at least the manifest bound
+  uint32_t maxdeg0 = d->m_max0;
+  {
+    const CozoGpuHnswLevel& l0 = d->levels[0];
+    for (uint32_t i = 0; i < n; ++i) maxdeg0 = std::max<uint32_t>(maxdeg0, (uint32_t)(l0.row_ptr[i + 1] - l0.row_ptr[i]));
+  }
+  uint32_t maxdegu = d->m_max;
+  for (uint32_t L = 1; L < d->n_levels; ++L) {
+    const CozoGpuHnswLevel& lv = d->levels[L];
+    if (!lv.node_ids) {
+      delete h;
+      return set_error(COZO_GPU_EINVAL, "layer -%u needs node_ids", L);
+    }
+    for (uint32_t i = 0; i < lv.n_nodes; ++i)
+      maxdegu = std::max<uint32_t>(maxdegu, (uint32_t)(lv.row_ptr[i + 1] - lv.row_ptr[i]));
+  }
+  g.s0 = round_up(std::max(maxdeg0, 1u), 32);
+  g.su = round_up(std::max(maxdegu, 1u), 32);
+
+  // node -> top layer
+  h->node_level.assign(n, 0);
+  for (uint32_t L = 1; L < d->n_levels; ++L) {
+    const CozoGpuHnswLevel& lv = d->levels[L];
+    for (uint32_t i = 0; i < lv.n_nodes; ++i) {
+      uint32_t id = lv.node_ids[i];
+      if (id >= n || h->node_level[id] != L - 1) {
+        delete h;
+        return set_error(COZO_GPU_EINVAL, "node %u on layer -%u is missing from layer -%u", id, L, L - 1);
+      }
+      h->node_level[id] = (uint8_t)L;
+    }
+  }
+  if (g.entry != NONE && h->node_level[g.entry] != g.top_level) {
+    delete h;
+    return set_error(COZO_GPU_EINVAL, "entry point must live on the top layer");
+  }
+  std::vector<uint32_t> upper_off(n, NONE);
+  uint64_t up_rows = 0;
+  for (uint32_t i = 0; i < n; ++i)
+    if (h->node_level[i]) {
+      upper_off[i] = (uint32_t)up_rows;
+      up_rows += h->node_level[i];
+    }
+  h->up_rows = up_rows;
+
+  auto fail = [&](int code) {
+    cozo_gpu_hnsw_free(h);
+    return code;
+  };
+#define STAGE_CUDA(call)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (call);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return fail(set_error(_e == cudaErrorMemoryAllocation ? COZO_GPU_ENOMEM : COZO_GPU_ECUDA,        \
+                            "%s failed: %s", #call, cudaGetErrorString(_e)));                         \
+  } while (0)
+
+  // vectors
+  if (n) {
+    STAGE_CUDA(cudaMalloc(&h->d_vec, (size_t)n * g.ld * 4));
+    if (g.ld != g.dim) STAGE_CUDA(cudaMemset(h->d_vec, 0, (size_t)n * g.ld * 4));
+    STAGE_CUDA(cudaMemcpy2D(h->d_vec, (size_t)g.ld * 4, d->vectors, (size_t)g.dim * 4, (size_t)g.dim * 4, n,
+                            d->vectors_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  }
+  g.vec = h->d_vec;
+  // layer 0 adjacency
+  {
+    std::vector<uint32_t> adj((size_t)n * g.s0, NONE);
+    const CozoGpuHnswLevel& l0 = d->levels[0];
+    for (uint32_t i = 0; i < n; ++i) {
+      uint64_t b = l0.row_ptr[i], e = l0.row_ptr[i + 1];
+      for (uint64_t kx = b; kx < e; ++kx) {
+        uint32_t t = l0.col_idx[kx];
+        if (t >= n) return fail(set_error(COZO_GPU_EINVAL, "layer 0 edge %u->%u out of range", i, t));
+        adj[(size_t)i * g.s0 + (kx - b)] = t;
+      }
+    }
+    if (n) {
+      STAGE_CUDA(cudaMalloc(&h->d_adj0, adj.size() * 4));
+      STAGE_CUDA(cudaMemcpy(h->d_adj0, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice));
+    }
+    g.adj0 = h->d_adj0;
+  }
+  // upper layers
+  {
+    std::vector<uint32_t> adj((size_t)std::max<uint64_t>(up_rows, 1) * g.su, NONE);
+    for (uint32_t L = 1; L < d->n_levels; ++L) {
+      const CozoGpuHnswLevel& lv = d->levels[L];
+      for (uint32_t i = 0; i < lv.n_nodes; ++i) {
+        uint32_t id = lv.node_ids[i];
+        uint64_t b = lv.row_ptr[i], e = lv.row_ptr[i + 1];
+        size_t row = (size_t)upper_off[id] + (L - 1);
+        for (uint64_t kx = b; kx < e; ++kx) {
+          uint32_t t = lv.col_idx[kx];
+          if (t >= n || h->node_level[t] < L)
+            return fail(set_error(COZO_GPU_EINVAL, "layer -%u edge %u->%u leaves the layer", L, id, t));
+          adj[row * g.su + (kx - b)] = t;
+        }
+      }
+    }
+    STAGE_CUDA(cudaMalloc(&h->d_adj_up, adj.size() * 4));
+    STAGE_CUDA(cudaMemcpy(h->d_adj_up, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice));
+    STAGE_CUDA(cudaMalloc(&h->d_upper_off, (size_t)std::max(n, 1u) * 4));
+    if (n) STAGE_CUDA(cudaMemcpy(h->d_upper_off, upper_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    g.adj_up = h->d_adj_up;
+    g.upper_off = h->d_upper_off;
+  }
+#undef STAGE_CUDA
+  *out = h;
+  return 0;
+}
+
+extern "C" void cozo_gpu_hnsw_free(cozo_gpu_hnsw_t* h) {
+  if (!h) return;
+  for (auto* ws : h->pool) free_ws(ws);
+  if (h->d_vec && h->vec_owned) cudaFree(h->d_vec);
+  if (h->d_adj0) cudaFree(h->d_adj0);
+  if (h->d_upper_off) cudaFree(h->d_upper_off);
+  if (h->d_adj_up) cudaFree(h->d_adj_up);
+  if (h->d_adj0_dist) cudaFree(h->d_adj0_dist);
+  if (h->d_adj_up_dist) cudaFree(h->d_adj_up_dist);
+  if (h->d_node_level) cudaFree(h->d_node_level);
+  delete h;
+}
+
+static int check_search_args(cozo_gpu_hnsw_t* h, uint32_t k, uint32_t ef) {
+  if (!h) return set_error(COZO_GPU_EINVAL, "null index handle");
+  // SearchInput::normalize_hnsw rejects k<=0 / ef<=0 (data/program.rs:1341-1569)
+  if (k == 0) return set_error(COZO_GPU_EINVAL, "k must be positive");
+  if (ef == 0) return set_error(COZO_GPU_EINVAL, "ef must be positive");
+  return 0;
+}
+
+extern "C" int cozo_gpu_hnsw_search_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k,
+                                        uint32_t ef, double radius, uint32_t* out_ids_dev, float* out_dist_dev,
+                                        uint32_t* out_count_dev, uint32_t* per_query_stats_dev, void* stream) {
+  int rc = check_search_args(h, k, ef);
+  if (rc) return rc;
+  if (B && (!queries_dev || !out_ids_dev || !out_dist_dev)) return set_error(COZO_GPU_EINVAL, "null buffer");
+  HnswWorkspace* ws = hnsw_acquire_ws(h);
+  if (!ws) return COZO_GPU_ECUDA;
+  rc = hnsw_launch_search(h, ws, queries_dev, B, k, ef, radius, out_ids_dev, out_dist_dev, out_count_dev,
+                          per_query_stats_dev, (cudaStream_t)stream);
+  // The workspace (visited bitmaps) stays in use until the kernel ends: hand it
+  // back to the pool from a host callback ordered after the kernel on `stream`,
+  // which keeps this call asynchronous.
+  struct Rel {
+    cozo_gpu_hnsw* h;
+    HnswWorkspace* ws;
+  };
+  if (rc == 0) {
+    auto* r = new Rel{h, ws};
+    cudaError_t e = cudaLaunchHostFunc(
+        (cudaStream_t)stream,
+        [](void* u) {
+          auto* r = static_cast<Rel*>(u);
+          hnsw_release_ws(r->h, r->ws);
+          delete r;
+        },
+        r);
+    if (e != cudaSuccess) {
+      delete r;
+      cudaStreamSynchronize((cudaStream_t)stream);
+      hnsw_release_ws(h, ws);
+      return set_error(COZO_GPU_ECUDA, "cudaLaunchHostFunc failed: %s", cudaGetErrorString(e));
+    }
+    return 0;
+  }
+  hnsw_release_ws(h, ws);
+  return rc;
+}
+
+extern "C" int cozo_gpu_hnsw_search(cozo_gpu_hnsw_t* h, const float* queries, uint32_t B, uint32_t k, uint32_t ef,
+                                    double radius, uint32_t* out_ids, float* out_dist, uint32_t* out_count,
+                                    CozoGpuSearchStats* stats) {
+  int rc = check_search_args(h, k, ef);
+  if (rc) return rc;
+  if (B && (!queries || !out_ids || !out_dist)) return set_error(COZO_GPU_EINVAL, "null buffer");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return 0;
+  HnswWorkspace* ws = hnsw_acquire_ws(h);
+  if (!ws) return COZO_GPU_ECUDA;
+  auto done = [&](int code) {
+    hnsw_release_ws(h, ws);
+    return code;
+  };
+#define S_CUDA(call)                                                                              \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return done(set_error(_e == cudaErrorMemoryAllocation ? COZO_GPU_ENOMEM : COZO_GPU_ECUDA,    \
+                            "%s failed: %s", #call, cudaGetErrorString(_e)));                     \
+  } while (0)
+  const uint32_t dim = h->dev.dim;
+  size_t qf = (size_t)B * dim;
+  if (ws->q_floats < qf) {
+    if (ws->q) cudaFree(ws->q);
+    ws->q = nullptr;
+    ws->q_floats = 0;
+    S_CUDA(cudaMalloc(&ws->q, qf * 4));
+    ws->q_floats = qf;
+  }
+  if (ws->out_rows < B || ws->out_k < k) {
+    if (ws->ids) cudaFree(ws->ids);
+    if (ws->dist) cudaFree(ws->dist);
+    if (ws->count) cudaFree(ws->count);
+    if (ws->qstats) cudaFree(ws->qstats);
+    ws->ids = nullptr;
+    ws->dist = nullptr;
+    ws->count = nullptr;
+    ws->qstats = nullptr;
+    ws->out_rows = ws->out_k = 0;
+    size_t rows = std::max<size_t>(B, ws->out_rows), kk = std::max<size_t>(k, ws->out_k);
+    S_CUDA(cudaMalloc(&ws->ids, rows * kk * 4));
+    S_CUDA(cudaMalloc(&ws->dist, rows * kk * 4));
+    S_CUDA(cudaMalloc(&ws->count, rows * 4));
+    S_CUDA(cudaMalloc(&ws->qstats, rows * 16));
+    ws->out_rows = rows;
+    ws->out_k = kk;
+  }
+  cudaStream_t st = ws->stream;
+  S_CUDA(cudaMemcpyAsync(ws->q, queries, qf * 4, cudaMemcpyHostToDevice, st));
+  S_CUDA(cudaEventRecord(ws->e0, st));
+  rc = hnsw_launch_search(h, ws, ws->q, B, k, ef, radius, ws->ids, ws->dist, ws->count, ws->qstats, st);
+  if (rc) return done(rc);
+  S_CUDA(cudaEventRecord(ws->e1, st));
+  S_CUDA(cudaMemcpyAsync(out_ids, ws->ids, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+  S_CUDA(cudaMemcpyAsync(out_dist, ws->dist, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+  if (out_count) S_CUDA(cudaMemcpyAsync(out_count, ws->count, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  std::vector<uint32_t> qs;
+  if (stats) {
+    qs.resize((size_t)B * 4);
+    S_CUDA(cudaMemcpyAsync(qs.data(), ws->qstats, (size_t)B * 16, cudaMemcpyDeviceToHost, st));
+  }
+  S_CUDA(cudaStreamSynchronize(st));
+  if (stats) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ws->e0, ws->e1);
+    stats->n_queries = B;
+    stats->kernel_ms = ms;
+    for (uint32_t i = 0; i < B; ++i) {
+      stats->dist_evals += qs[(size_t)i * 4 + 0];
+      stats->nodes_expanded += qs[(size_t)i * 4 + 1];
+      stats->nbr_reads += qs[(size_t)i * 4 + 2];
+    }
+  }
+#undef S_CUDA
+  return done(0);
+}
+
+extern "C" int cozo_gpu_hnsw_info(cozo_gpu_hnsw_t* h, uint32_t* n_vectors, uint32_t* dim, uint32_t* n_levels,
+                                  uint32_t* entry_point) {
+  if (!h) return set_error(COZO_GPU_EINVAL, "null index handle");
+  if (n_vectors) *n_vectors = h->dev.n;
+  if (dim) *dim = h->dev.dim;
+  if (n_levels) *n_levels = h->n_levels;
+  if (entry_point) *entry_point = h->dev.entry;
+  return 0;
+}
+
+extern "C" const float* cozo_gpu_hnsw_vectors_dev(cozo_gpu_hnsw_t* h, uint32_t* row_stride) {
+  if (!h) return nullptr;
+  if (row_stride) *row_stride = h->dev.ld;
+  return h->dev.vec;
+}
+
+// download one layer as CSR with rows sorted ascending (key order)
+static int fetch_level(cozo_gpu_hnsw_t* h, uint32_t level, std::vector<uint32_t>& node_ids,
+                       std::vector<uint64_t>& row_ptr, std::vector<uint32_t>& col_idx) {
+  const HnswDev& g = h->dev;
+  if (level >= h->n_levels) return set_error(COZO_GPU_EINVAL, "layer %u does not exist", level);
+  node_ids.clear();
+  row_ptr.assign(1, 0);
+  col_idx.clear();
+  if (level == 0) {
+    std::vector<uint32_t> adj((size_t)g.n * g.s0);
+    if (g.n) COZO_CUDA(cudaMemcpy(adj.data(), g.adj0, adj.size() * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < g.n; ++i) {
+      node_ids.push_back(i);
+      size_t b = col_idx.size();
+      for (uint32_t j = 0; j < g.s0; ++j) {
+        uint32_t t = adj[(size_t)i * g.s0 + j];
+        if (t == NONE) break;
+        col_idx.push_back(t);
+      }
+      std::sort(col_idx.begin() + b, col_idx.end());
+      row_ptr.push_back(col_idx.size());
+    }
+  } else {
+    std::vector<uint32_t> adj((size_t)std::max<uint64_t>(h->up_rows, 1) * g.su);
+    std::vector<uint32_t> off(g.n);
+    COZO_CUDA(cudaMemcpy(adj.data(), g.adj_up, adj.size() * 4, cudaMemcpyDeviceToHost));
+    if (g.n) COZO_CUDA(cudaMemcpy(off.data(), g.upper_off, (size_t)g.n * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < g.n; ++i) {
+      if (h->node_level[i] < level) continue;
+      node_ids.push_back(i);
+      size_t b = col_idx.size();
+      size_t row = (size_t)off[i] + level - 1;
+      for (uint32_t j = 0; j < g.su; ++j) {
+        uint32_t t = adj[row * g.su + j];
+        if (t == NONE) break;
+        col_idx.push_back(t);
+      }
+      std::sort(col_idx.begin() + b, col_idx.end());
+      row_ptr.push_back(col_idx.size());
+    }
+  }
+  return 0;
+}
+
+extern "C" int cozo_gpu_hnsw_level_size(cozo_gpu_hnsw_t* h, uint32_t level, uint32_t* n_nodes, uint64_t* n_edges) {
+  if (!h) return set_error(COZO_GPU_EINVAL, "null index handle");
+  std::vector<uint32_t> ni, ci;
+  std::vector<uint64_t> rp;
+  int rc = fetch_level(h, level, ni, rp, ci);
+  if (rc) return rc;
+  if (n_nodes) *n_nodes = (uint32_t)ni.size();
+  if (n_edges) *n_edges = ci.size();
+  return 0;
+}
+
+extern "C" int cozo_gpu_hnsw_export_level(cozo_gpu_hnsw_t* h, uint32_t level, uint32_t* node_ids, uint64_t* row_ptr,
+                                          uint32_t* col_idx) {
+  if (!h) return set_error(COZO_GPU_EINVAL, "null index handle");
+  std::vector<uint32_t> ni, ci;
+  std::vector<uint64_t> rp;
+  int rc = fetch_level(h, level, ni, rp, ci);
+  if (rc) return rc;
+  if (node_ids) std::copy(ni.begin(), ni.end(), node_ids);
+  if (row_ptr) std::copy(rp.begin(), rp.end(), row_ptr);
+  if (col_idx) std::copy(ci.begin(), ci.end(), col_idx);
+  return 0;
+}

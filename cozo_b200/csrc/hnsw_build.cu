@@ -1,0 +1,686 @@
+// hnsw_build.cu — index construction on the device.
+//
+// Batched variant of SessionTx::hnsw_put_vector (runtime/hnsw.rs:155-375):
+// nodes are inserted in id order like create_hnsw_index's bulk insert
+// (runtime/relation.rs:1176-1185), a batch at a time.  Every node of a batch
+//   K1  searches the graph as it stood before the batch: ef=1 on the layers
+//       above its own (hnsw.rs:219-229), ef_construction on its own layers
+//       (hnsw.rs:242-256; found_nn carries over between layers);
+//   K2  picks neighbours with hnsw_select_neighbours_heuristic (hnsw.rs:470-538),
+//       capped at m_max(layer) (hnsw.rs:243-247), writes its own adjacency row
+//       (the out edges, hnsw.rs:281-298) and queues the in edges (hnsw.rs:300-318);
+//   K3  sorts the queued in edges by (layer, target);
+//   K4  appends them to the target rows, shrinking an over-full row with the
+//       same heuristic over the stored distances (hnsw_shrink_neighbour,
+//       hnsw.rs:376-469).
+// Differences from the reference, all consequences of batching: nodes of one
+// batch do not see each other during K1, and a row that receives several in
+// edges in one batch is shrunk once per chunk of 32 arrivals rather than once
+// per arrival.  Soft-deleted (`ignore_link`) rows are not materialised: the
+// staged layout only holds what hnsw_get_neighbours would return.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "hnsw_host.hpp"
+
+namespace cozo {
+
+struct SmemLayout {
+  uint32_t off_fi, off_pend, off_bars, off_ring, warp_bytes;
+};
+static SmemLayout make_layout(uint32_t ef, uint32_t ns, uint32_t ld) {
+  SmemLayout l;
+  uint32_t efcap = round_up(ef, 32);
+  l.off_fi = efcap * 4;
+  l.off_pend = l.off_fi + efcap * 4;
+  l.off_bars = l.off_pend + 32 * 4;
+  l.off_ring = round_up(l.off_bars + ns * 8, 128);
+  l.warp_bytes = round_up(l.off_ring + ns * ld * 4, 128);
+  return l;
+}
+
+struct BuildDev {
+  uint32_t* adj0;
+  float* adj0_d;
+  uint32_t* deg0;
+  uint32_t* adj_up;
+  float* adj_up_d;
+  uint32_t* deg_up;
+  const uint8_t* node_level;
+  uint32_t m_max0, m_max;
+  int keep_pruned;
+};
+
+struct BatchParams {
+  uint32_t begin, count;  // node ids [begin, begin+count)
+  uint32_t top;           // top layer before the batch
+  uint32_t ef_c;
+  const uint32_t* coff;        // [count+1] first candidate list of node i
+  const uint32_t* list_node;   // [T]
+  const uint32_t* list_level;  // [T]
+  uint32_t T;
+  float* cand_d;       // [T x ef_c] ascending
+  uint32_t* cand_id;   // [T x ef_c]
+  uint32_t* cand_cnt;  // [T]
+  // in-edge queue
+  unsigned long long* req_key;  // (layer << 32) | target
+  uint32_t* req_src;
+  float* req_d;
+  uint32_t* req_count;
+  // workspace
+  uint32_t* counter;
+  uint32_t* vis;
+  uint32_t nwords;
+  uint32_t* vlog;
+  uint32_t logcap;
+  uint32_t ns;
+  SmemLayout lay;
+};
+
+// K1 ------------------------------------------------------------------------
+template <int NV, int METRIC>
+__global__ void __launch_bounds__(256, 2) build_search_kernel(HnswDev g, BuildDev b, BatchParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+  uint8_t* base = smem + (size_t)warp * p.lay.warp_bytes;
+  WarpCtx w;
+  w.fd = reinterpret_cast<float*>(base);
+  w.fi = reinterpret_cast<uint32_t*>(base + p.lay.off_fi);
+  w.pend = reinterpret_cast<uint32_t*>(base + p.lay.off_pend);
+  w.bars = reinterpret_cast<uint64_t*>(base + p.lay.off_bars);
+  w.ring = reinterpret_cast<float*>(base + p.lay.off_ring);
+  const size_t slot = (size_t)blockIdx.x * wpc + warp;
+  w.vis = p.vis + slot * p.nwords;
+  w.nwords = p.nwords;
+  w.vlog = p.vlog + slot * p.logcap;
+  w.logcap = p.logcap;
+  w.ns = p.ns;
+  w.nlog = 0;
+  w.head = 0;
+  w.phase = 0;
+  if (lane == 0) {
+    for (uint32_t s = 0; s < p.ns; ++s) mbar_init(&w.bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const int nvec4 = g.ld >> 2;
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(p.counter, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= p.count) break;
+    const uint32_t id = p.begin + i;
+    const uint32_t lq = b.node_level[id];
+    float4 q[NV];
+    float qnorm;
+    load_query<NV>(g.vec + (size_t)id * g.ld, g.ld, lane, q, qnorm);
+    float d = dist_ldg1<NV, METRIC>(q, reinterpret_cast<const float4*>(g.vec + (size_t)g.entry * g.ld), lane, nvec4,
+                                    qnorm);
+    if (lane == 0) {
+      w.fd[0] = d;
+      w.fi[0] = g.entry;
+    }
+    w.len = 1;
+    w.cursor = 0;
+    w.dist_evals = w.nodes_expanded = w.nbr_reads = 0;
+    __syncwarp();
+    for (uint32_t L = p.top; L > lq; --L) search_level<NV, METRIC, true>(g, w, q, qnorm, 1, L, lane);
+    uint32_t L = lq < p.top ? lq : p.top;
+    const uint32_t l0 = p.coff[i];
+    for (;; --L) {
+      search_level<NV, METRIC, true>(g, w, q, qnorm, p.ef_c, L, lane);
+      const size_t list = (size_t)(l0 + L) * p.ef_c;
+      for (uint32_t j = lane; j < w.len; j += 32) {
+        p.cand_d[list + j] = w.fd[j];
+        p.cand_id[list + j] = w.fi[j] & IDMASK;
+      }
+      if (lane == 0) p.cand_cnt[l0 + L] = w.len;
+      __syncwarp();
+      if (L == 0) break;
+    }
+  }
+}
+
+// hnsw_select_neighbours_heuristic (hnsw.rs:470-538) over candidates sorted by
+// ascending distance to the base vector.  `cd/cid` may live in global or shared
+// memory; bit31 of cid is set on selected entries.  Returns |ret|.
+template <int NV, int METRIC>
+__device__ __forceinline__ uint32_t heuristic_select(const HnswDev& g, const float* cd, uint32_t* cid, uint32_t cnt,
+                                                     uint32_t mm, bool keep_pruned, uint32_t* sel_id, float* sel_d,
+                                                     int lane) {
+  const int nvec4 = g.ld >> 2;
+  uint32_t ns = 0;
+  uint32_t c = 0;
+  for (; c < cnt && ns < mm; ++c) {  // hnsw.rs:512
+    const uint32_t id = cid[c] & IDMASK;
+    const float dq = cd[c];
+    float4 cv[NV];
+    float cnorm;
+    load_query<NV>(g.vec + (size_t)id * g.ld, g.ld, lane, cv, cnorm);
+    bool add = true;
+    for (uint32_t e = 0; e < ns; ++e) {  // hnsw.rs:515-523
+      float de = dist_ldg1<NV, METRIC>(cv, reinterpret_cast<const float4*>(g.vec + (size_t)sel_id[e] * g.ld), lane,
+                                       nvec4, cnorm);
+      if (de < dq) {
+        add = false;
+        break;
+      }
+    }
+    if (add) {
+      if (lane == 0) {
+        sel_id[ns] = id;
+        sel_d[ns] = dq;
+        cid[c] = id | EXPANDED;
+      }
+      ++ns;
+      __syncwarp();
+    }
+  }
+  if (keep_pruned && c == cnt) {  // discarded back-fill, nearest first (hnsw.rs:530-536)
+    for (uint32_t j = 0; j < cnt && ns < mm; ++j) {
+      uint32_t v = cid[j];
+      if (v & EXPANDED) continue;
+      if (lane == 0) {
+        sel_id[ns] = v;
+        sel_d[ns] = cd[j];
+      }
+      ++ns;
+    }
+    __syncwarp();
+  }
+  return ns;
+}
+
+__device__ __forceinline__ void adj_row(const HnswDev& g, const BuildDev& b, uint32_t node, uint32_t level,
+                                        uint32_t*& ids, float*& ds, uint32_t*& deg, uint32_t& stride, uint32_t& mm) {
+  if (level == 0) {
+    ids = b.adj0 + (size_t)node * g.s0;
+    ds = b.adj0_d + (size_t)node * g.s0;
+    deg = b.deg0 + node;
+    stride = g.s0;
+    mm = b.m_max0;
+  } else {
+    size_t row = (size_t)g.upper_off[node] + level - 1;
+    ids = b.adj_up + row * g.su;
+    ds = b.adj_up_d + row * g.su;
+    deg = b.deg_up + row;
+    stride = g.su;
+    mm = b.m_max;
+  }
+}
+
+// K2 ------------------------------------------------------------------------
+template <int NV, int METRIC>
+__global__ void __launch_bounds__(128) build_select_kernel(HnswDev g, BuildDev b, BatchParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t mcap = b.m_max0 > b.m_max ? b.m_max0 : b.m_max;
+  uint32_t* sel_id = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * 2 * mcap;
+  float* sel_d = reinterpret_cast<float*>(sel_id + mcap);
+  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= p.T) return;
+  const uint32_t node = p.list_node[t], level = p.list_level[t];
+  uint32_t *ids, *deg;
+  float* ds;
+  uint32_t stride, mm;
+  adj_row(g, b, node, level, ids, ds, deg, stride, mm);
+  const size_t list = (size_t)t * p.ef_c;
+  uint32_t ns = heuristic_select<NV, METRIC>(g, p.cand_d + list, p.cand_id + list, p.cand_cnt[t], mm,
+                                             b.keep_pruned != 0, sel_id, sel_d, lane);
+  __syncwarp();
+  uint32_t rbase = 0;
+  if (lane == 0) {
+    *deg = ns;
+    rbase = atomicAdd(p.req_count, ns);
+  }
+  rbase = __shfl_sync(0xffffffffu, rbase, 0);
+  for (uint32_t j = lane; j < ns; j += 32) {
+    ids[j] = sel_id[j];  // out edge (hnsw.rs:281-298)
+    ds[j] = sel_d[j];
+    p.req_key[rbase + j] = ((unsigned long long)level << 32) | sel_id[j];  // in edge (hnsw.rs:300-318)
+    p.req_src[rbase + j] = node;
+    p.req_d[rbase + j] = sel_d[j];
+  }
+}
+
+// segment heads of the sorted in-edge queue
+__global__ void build_heads_kernel(const unsigned long long* keys, uint32_t n, uint32_t* heads, uint32_t* nheads) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  if (r == 0 || keys[r] != keys[r - 1]) heads[atomicAdd(nheads, 1u)] = r;
+}
+
+// K4 ------------------------------------------------------------------------
+template <int NV, int METRIC>
+__global__ void __launch_bounds__(128) build_link_kernel(HnswDev g, BuildDev b, const unsigned long long* keys,
+                                                         const uint32_t* perm, const uint32_t* req_src,
+                                                         const float* req_d, uint32_t nreq, const uint32_t* heads,
+                                                         uint32_t nheads) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t mcap = b.m_max0 > b.m_max ? b.m_max0 : b.m_max;
+  const uint32_t ucap = mcap + 32;
+  // per warp: u_id,u_d,s_id,s_d [ucap] ; sel_id, sel_d [mcap]
+  uint32_t* wbase = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * (4 * ucap + 2 * mcap);
+  uint32_t* u_id = wbase;
+  float* u_d = reinterpret_cast<float*>(wbase + ucap);
+  uint32_t* s_id = wbase + 2 * ucap;
+  float* s_d = reinterpret_cast<float*>(wbase + 3 * ucap);
+  uint32_t* sel_id = wbase + 4 * ucap;
+  float* sel_d = reinterpret_cast<float*>(wbase + 4 * ucap + mcap);
+  const uint32_t h = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (h >= nheads) return;
+  const uint32_t start = heads[h];
+  const unsigned long long key = keys[start];
+  const uint32_t level = (uint32_t)(key >> 32), node = (uint32_t)(key & 0xFFFFFFFFull);
+  uint32_t end = start + 1;
+  while (end < nreq && keys[end] == key) ++end;
+  uint32_t *ids, *degp;
+  float* ds;
+  uint32_t stride, mm;
+  adj_row(g, b, node, level, ids, ds, degp, stride, mm);
+  uint32_t deg = *degp;
+  for (uint32_t a0 = start; a0 < end; a0 += 32) {
+    const uint32_t na = min(32u, end - a0);
+    uint32_t asrc = NONE;
+    float ad = 0.f;
+    if ((uint32_t)lane < na) {
+      uint32_t r = perm[a0 + lane];
+      asrc = req_src[r];
+      ad = req_d[r];
+    }
+    if (deg + na <= mm) {  // plain append (hnsw.rs:338-339 not exceeded)
+      if ((uint32_t)lane < na) {
+        ids[deg + lane] = asrc;
+        ds[deg + lane] = ad;
+      }
+      deg += na;
+      __syncwarp();
+      continue;
+    }
+    // shrink (hnsw.rs:376-469): candidates = stored out-neighbours + arrivals
+    const uint32_t nc = deg + na;
+    for (uint32_t j = lane; j < deg; j += 32) {
+      u_id[j] = ids[j];
+      u_d[j] = ds[j];
+    }
+    if ((uint32_t)lane < na) {
+      u_id[deg + lane] = asrc;
+      u_d[deg + lane] = ad;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < nc; j += 32) {  // rank sort by (distance, position)
+      float dj = u_d[j];
+      uint32_t rank = 0;
+      for (uint32_t x = 0; x < nc; ++x) {
+        float dx = u_d[x];
+        rank += (dx < dj) || (dx == dj && x < j);
+      }
+      s_id[rank] = u_id[j];
+      s_d[rank] = dj;
+    }
+    __syncwarp();
+    uint32_t ns = heuristic_select<NV, METRIC>(g, s_d, s_id, nc, mm, b.keep_pruned != 0, sel_id, sel_d, lane);
+    __syncwarp();
+    for (uint32_t j = lane; j < stride; j += 32) {
+      bool in = j < ns;
+      if (in || j < nc) {
+        ids[j] = in ? sel_id[j] : NONE;
+        ds[j] = in ? sel_d[j] : 0.f;
+      }
+    }
+    deg = ns;
+    __syncwarp();
+  }
+  if (lane == 0) *degp = deg;
+}
+
+template <int NV>
+struct BuildKernels {
+  static void get(int metric, void (*&k1)(HnswDev, BuildDev, BatchParams), void (*&k2)(HnswDev, BuildDev, BatchParams),
+                  void (*&k4)(HnswDev, BuildDev, const unsigned long long*, const uint32_t*, const uint32_t*,
+                              const float*, uint32_t, const uint32_t*, uint32_t)) {
+    switch (metric) {
+      case COZO_GPU_L2:
+        k1 = build_search_kernel<NV, COZO_GPU_L2>;
+        k2 = build_select_kernel<NV, COZO_GPU_L2>;
+        k4 = build_link_kernel<NV, COZO_GPU_L2>;
+        break;
+      case COZO_GPU_COSINE:
+        k1 = build_search_kernel<NV, COZO_GPU_COSINE>;
+        k2 = build_select_kernel<NV, COZO_GPU_COSINE>;
+        k4 = build_link_kernel<NV, COZO_GPU_COSINE>;
+        break;
+      default:
+        k1 = build_search_kernel<NV, COZO_GPU_IP>;
+        k2 = build_select_kernel<NV, COZO_GPU_IP>;
+        k4 = build_link_kernel<NV, COZO_GPU_IP>;
+    }
+  }
+};
+
+struct SplitMix64 {
+  uint64_t s;
+  uint64_t next() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+}  // namespace cozo
+
+using namespace cozo;
+
+extern "C" int cozo_gpu_hnsw_build(cozo_gpu_hnsw_t** out, const CozoGpuHnswBuildDesc* d) {
+  if (!out || !d) return set_error(COZO_GPU_EINVAL, "null argument");
+  *out = nullptr;
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (d->dim == 0 || d->n_vectors == 0 || !d->vectors) return set_error(COZO_GPU_EINVAL, "bad build descriptor");
+  if (d->metric < 0 || d->metric > 2) return set_error(COZO_GPU_EINVAL, "unknown distance %d", d->metric);
+  if (d->m_neighbours < 2 || d->m_neighbours > 64)
+    return set_error(COZO_GPU_EUNSUP, "m_neighbours must be in [2,64] for the device builder");
+  if (d->ef_construction == 0) return set_error(COZO_GPU_EINVAL, "ef_construction must be set");  // sys.rs:603
+  if (d->extend_candidates) return set_error(COZO_GPU_EUNSUP, "extend_candidates is not supported by the device builder");
+  if (d->n_vectors >= 0x7FFFFFFFu) return set_error(COZO_GPU_EUNSUP, "too many vectors");
+  const DeviceInfo& di = device_info();
+  const uint32_t n = d->n_vectors;
+  const uint32_t m = d->m_neighbours;
+
+  auto* h = new cozo_gpu_hnsw();
+  HnswDev& g = h->dev;
+  g.n = n;
+  g.dim = d->dim;
+  g.ld = round_up(d->dim, 4);
+  g.metric = d->metric;
+  h->m_max = m;       // relation.rs:1145
+  h->m_max0 = 2 * m;  // relation.rs:1146
+  g.s0 = round_up(h->m_max0, 32);
+  g.su = round_up(h->m_max, 32);
+
+  auto fail = [&](int code) {
+    cozo_gpu_hnsw_free(h);
+    return code;
+  };
+#define B_CUDA(call)                                                                                \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(set_error(_e == cudaErrorMemoryAllocation ? COZO_GPU_ENOMEM : COZO_GPU_ECUDA,      \
+                            "%s failed: %s (line %d)", #call, cudaGetErrorString(_e), __LINE__));   \
+  } while (0)
+
+  // level law (hnsw.rs:46-52), level_multiplier = 1/ln(m) (relation.rs:1147)
+  h->node_level.assign(n, 0);
+  {
+    SplitMix64 rng{d->level_seed};
+    const double mult = 1.0 / std::log((double)m);
+    for (uint32_t i = 0; i < n; ++i) {
+      double u = rng.uniform();
+      double r = -std::log(u) * mult;
+      if (!(r < 15.0)) r = 15.0;
+      h->node_level[i] = (uint8_t)std::floor(r);
+    }
+  }
+  std::vector<uint32_t> upper_off(n, NONE);
+  uint64_t up_rows = 0;
+  for (uint32_t i = 0; i < n; ++i)
+    if (h->node_level[i]) {
+      upper_off[i] = (uint32_t)up_rows;
+      up_rows += h->node_level[i];
+    }
+  h->up_rows = up_rows;
+  const uint64_t up_alloc = std::max<uint64_t>(up_rows, 1);
+
+  // vectors
+  if (d->vectors_on_device && d->borrow_vectors && g.ld == g.dim) {
+    h->d_vec = const_cast<float*>(d->vectors);
+    h->vec_owned = false;
+  } else {
+    B_CUDA(cudaMalloc(&h->d_vec, (size_t)n * g.ld * 4));
+    if (g.ld != g.dim) B_CUDA(cudaMemset(h->d_vec, 0, (size_t)n * g.ld * 4));
+    B_CUDA(cudaMemcpy2D(h->d_vec, (size_t)g.ld * 4, d->vectors, (size_t)g.dim * 4, (size_t)g.dim * 4, n,
+                        d->vectors_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  }
+  g.vec = h->d_vec;
+  uint32_t *d_deg0 = nullptr, *d_deg_up = nullptr;
+  B_CUDA(cudaMalloc(&h->d_adj0, (size_t)n * g.s0 * 4));
+  B_CUDA(cudaMemset(h->d_adj0, 0xFF, (size_t)n * g.s0 * 4));
+  B_CUDA(cudaMalloc(&h->d_adj0_dist, (size_t)n * g.s0 * 4));
+  B_CUDA(cudaMalloc(&h->d_adj_up, up_alloc * g.su * 4));
+  B_CUDA(cudaMemset(h->d_adj_up, 0xFF, up_alloc * g.su * 4));
+  B_CUDA(cudaMalloc(&h->d_adj_up_dist, up_alloc * g.su * 4));
+  B_CUDA(cudaMalloc(&h->d_upper_off, (size_t)n * 4));
+  B_CUDA(cudaMemcpy(h->d_upper_off, upper_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+  B_CUDA(cudaMalloc(&h->d_node_level, n));
+  B_CUDA(cudaMemcpy(h->d_node_level, h->node_level.data(), n, cudaMemcpyHostToDevice));
+  g.adj0 = h->d_adj0;
+  g.adj_up = h->d_adj_up;
+  g.upper_off = h->d_upper_off;
+
+  struct Scratch {
+    uint32_t *deg0 = nullptr, *deg_up = nullptr;
+    uint32_t *coff = nullptr, *list_node = nullptr, *list_level = nullptr;
+    float* cand_d = nullptr;
+    uint32_t *cand_id = nullptr, *cand_cnt = nullptr;
+    unsigned long long *req_key = nullptr, *req_key2 = nullptr;
+    uint32_t *req_src = nullptr, *perm = nullptr, *perm2 = nullptr, *heads = nullptr, *counters = nullptr;
+    float* req_d = nullptr;
+    void* cub_tmp = nullptr;
+    ~Scratch() {
+      void* ptrs[] = {deg0, deg_up, coff, list_node, list_level, cand_d, cand_id, cand_cnt, req_key, req_key2,
+                      req_src, perm, perm2, heads, counters, req_d, cub_tmp};
+      for (void* p : ptrs)
+        if (p) cudaFree(p);
+    }
+  } sc;
+  (void)d_deg0;
+  (void)d_deg_up;
+  B_CUDA(cudaMalloc(&sc.deg0, (size_t)n * 4));
+  B_CUDA(cudaMemset(sc.deg0, 0, (size_t)n * 4));
+  B_CUDA(cudaMalloc(&sc.deg_up, up_alloc * 4));
+  B_CUDA(cudaMemset(sc.deg_up, 0, up_alloc * 4));
+
+  BuildDev b{};
+  b.adj0 = h->d_adj0;
+  b.adj0_d = h->d_adj0_dist;
+  b.deg0 = sc.deg0;
+  b.adj_up = h->d_adj_up;
+  b.adj_up_d = h->d_adj_up_dist;
+  b.deg_up = sc.deg_up;
+  b.node_level = h->d_node_level;
+  b.m_max0 = h->m_max0;
+  b.m_max = h->m_max;
+  b.keep_pruned = d->keep_pruned_connections;
+
+  void (*k1)(HnswDev, BuildDev, BatchParams) = nullptr;
+  void (*k2)(HnswDev, BuildDev, BatchParams) = nullptr;
+  void (*k4)(HnswDev, BuildDev, const unsigned long long*, const uint32_t*, const uint32_t*, const float*, uint32_t,
+             const uint32_t*, uint32_t) = nullptr;
+  {
+    uint32_t need = (g.ld / 4 + 31) / 32;
+    if (need <= 1) BuildKernels<1>::get(g.metric, k1, k2, k4);
+    else if (need <= 2) BuildKernels<2>::get(g.metric, k1, k2, k4);
+    else if (need <= 4) BuildKernels<4>::get(g.metric, k1, k2, k4);
+    else if (need <= 6) BuildKernels<6>::get(g.metric, k1, k2, k4);
+    else if (need <= 8) BuildKernels<8>::get(g.metric, k1, k2, k4);
+    else if (need <= 16) BuildKernels<16>::get(g.metric, k1, k2, k4);
+    else return fail(set_error(COZO_GPU_EUNSUP, "vec_dim %u exceeds the supported maximum 2048", g.dim));
+  }
+
+  const uint32_t ef_c = d->ef_construction;
+  uint32_t max_batch = d->max_batch ? d->max_batch : 8192;
+  uint32_t wpc = (uint32_t)get_option("hnsw.warps_per_cta", 4);
+  wpc = std::min(8u, std::max(1u, wpc));
+  uint32_t ns = (uint32_t)get_option("hnsw.stages", 4);
+  ns = std::min(32u, std::max(1u, ns));
+  SmemLayout lay = make_layout(ef_c, ns, g.ld);
+  size_t smem1 = (size_t)lay.warp_bytes * wpc;
+  while (smem1 > di.smem_optin && wpc > 1) {
+    wpc >>= 1;
+    smem1 = (size_t)lay.warp_bytes * wpc;
+  }
+  if (smem1 > di.smem_optin) return fail(set_error(COZO_GPU_EUNSUP, "ef_construction=%u does not fit shared memory", ef_c));
+  B_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  int cps = 0;
+  B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k1, wpc * 32, smem1));
+  if (cps < 1) return fail(set_error(COZO_GPU_ECUDA, "build kernel does not fit on an SM"));
+  const uint32_t max_grid1 = (uint32_t)di.sm_count * (uint32_t)cps;
+  const uint32_t mcap = std::max(h->m_max0, h->m_max);
+  const size_t smem2 = (size_t)4 * 2 * mcap * 4;
+  const size_t smem4 = (size_t)4 * (4 * (mcap + 32) + 2 * mcap) * 4;
+
+  HnswWorkspace* ws = hnsw_acquire_ws(h);
+  if (!ws) return fail(COZO_GPU_ECUDA);
+  auto fail_ws = [&](int code) {
+    hnsw_release_ws(h, ws);
+    return fail(code);
+  };
+#undef B_CUDA
+#define B_CUDA(call)                                                                                \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail_ws(set_error(_e == cudaErrorMemoryAllocation ? COZO_GPU_ENOMEM : COZO_GPU_ECUDA,   \
+                               "%s failed: %s (line %d)", #call, cudaGetErrorString(_e), __LINE__)); \
+  } while (0)
+  cudaStream_t st = ws->stream;
+  const uint32_t nwords = round_up((n + 31) / 32, 4);
+  const uint32_t logcap = std::min<uint32_t>(65536u, std::max<uint32_t>(4096u, 64u * ef_c));
+  {
+    size_t slots = (size_t)max_grid1 * wpc;
+    rc = hnsw_ws_reserve(ws, slots * nwords, slots * logcap);
+    if (rc) return fail_ws(rc);
+  }
+  // per-batch scratch sized for the largest batch
+  const uint32_t maxT = max_batch * 16;  // every node could own up to 16 layers
+  uint32_t Tcap = std::min<uint64_t>(maxT, (uint64_t)max_batch + up_rows + 16);
+  const uint64_t req_cap = (uint64_t)Tcap * mcap;
+  B_CUDA(cudaMalloc(&sc.coff, ((size_t)max_batch + 1) * 4));
+  B_CUDA(cudaMalloc(&sc.list_node, (size_t)Tcap * 4));
+  B_CUDA(cudaMalloc(&sc.list_level, (size_t)Tcap * 4));
+  B_CUDA(cudaMalloc(&sc.cand_d, (size_t)Tcap * ef_c * 4));
+  B_CUDA(cudaMalloc(&sc.cand_id, (size_t)Tcap * ef_c * 4));
+  B_CUDA(cudaMalloc(&sc.cand_cnt, (size_t)Tcap * 4));
+  B_CUDA(cudaMalloc(&sc.req_key, req_cap * 8));
+  B_CUDA(cudaMalloc(&sc.req_key2, req_cap * 8));
+  B_CUDA(cudaMalloc(&sc.req_src, req_cap * 4));
+  B_CUDA(cudaMalloc(&sc.req_d, req_cap * 4));
+  B_CUDA(cudaMalloc(&sc.perm, req_cap * 4));
+  B_CUDA(cudaMalloc(&sc.perm2, req_cap * 4));
+  B_CUDA(cudaMalloc(&sc.heads, req_cap * 4));
+  B_CUDA(cudaMalloc(&sc.counters, 64));
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, sc.req_key, sc.req_key2, sc.perm, sc.perm2, (int)req_cap, 0, 40,
+                                  st);
+  B_CUDA(cudaMalloc(&sc.cub_tmp, cub_bytes));
+  {
+    std::vector<uint32_t> iota(req_cap);
+    for (uint64_t i = 0; i < req_cap; ++i) iota[i] = (uint32_t)i;
+    B_CUDA(cudaMemcpy(sc.perm, iota.data(), req_cap * 4, cudaMemcpyHostToDevice));
+  }
+
+  // first vector: fresh self-loops only (hnsw.rs:360-373)
+  g.entry = 0;
+  g.top_level = h->node_level[0];
+  uint32_t inserted = 1;
+  std::vector<uint32_t> coff, lnode, llevel;
+  while (inserted < n) {
+    uint32_t bs = std::min<uint32_t>(std::min<uint32_t>(max_batch, std::max<uint32_t>(1u, inserted / 16)), n - inserted);
+    const uint32_t top = g.top_level;
+    coff.assign(bs + 1, 0);
+    lnode.clear();
+    llevel.clear();
+    for (uint32_t i = 0; i < bs; ++i) {
+      uint32_t id = inserted + i;
+      uint32_t nl = std::min<uint32_t>(h->node_level[id], top) + 1;
+      coff[i] = (uint32_t)lnode.size();
+      for (uint32_t L = 0; L < nl; ++L) {
+        lnode.push_back(id);
+        llevel.push_back(L);
+      }
+    }
+    coff[bs] = (uint32_t)lnode.size();
+    const uint32_t T = (uint32_t)lnode.size();
+    if (T > Tcap) return fail_ws(set_error(COZO_GPU_ECUDA, "internal: batch list overflow"));
+    B_CUDA(cudaMemcpyAsync(sc.coff, coff.data(), ((size_t)bs + 1) * 4, cudaMemcpyHostToDevice, st));
+    B_CUDA(cudaMemcpyAsync(sc.list_node, lnode.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    B_CUDA(cudaMemcpyAsync(sc.list_level, llevel.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    B_CUDA(cudaMemsetAsync(sc.counters, 0, 64, st));
+    BatchParams p{};
+    p.begin = inserted;
+    p.count = bs;
+    p.top = top;
+    p.ef_c = ef_c;
+    p.coff = sc.coff;
+    p.list_node = sc.list_node;
+    p.list_level = sc.list_level;
+    p.T = T;
+    p.cand_d = sc.cand_d;
+    p.cand_id = sc.cand_id;
+    p.cand_cnt = sc.cand_cnt;
+    p.req_key = sc.req_key;
+    p.req_src = sc.req_src;
+    p.req_d = sc.req_d;
+    p.req_count = sc.counters + 1;
+    p.counter = sc.counters + 0;
+    p.vis = ws->vis;
+    p.nwords = nwords;
+    p.vlog = ws->vlog;
+    p.logcap = logcap;
+    p.ns = ns;
+    p.lay = lay;
+    uint32_t grid1 = std::min<uint32_t>(max_grid1, (bs + wpc - 1) / wpc);
+    k1<<<grid1, wpc * 32, smem1, st>>>(g, b, p);
+    B_CUDA(cudaGetLastError());
+    k2<<<(T + 3) / 4, 128, smem2, st>>>(g, b, p);
+    B_CUDA(cudaGetLastError());
+    uint32_t nreq = 0;
+    B_CUDA(cudaMemcpyAsync(&nreq, sc.counters + 1, 4, cudaMemcpyDeviceToHost, st));
+    B_CUDA(cudaStreamSynchronize(st));
+    if (nreq > req_cap) return fail_ws(set_error(COZO_GPU_ECUDA, "internal: in-edge queue overflow"));
+    if (nreq) {
+      size_t tb = cub_bytes;
+      cub::DeviceRadixSort::SortPairs(sc.cub_tmp, tb, sc.req_key, sc.req_key2, sc.perm, sc.perm2, (int)nreq, 0, 40, st);
+      build_heads_kernel<<<(nreq + 255) / 256, 256, 0, st>>>(sc.req_key2, nreq, sc.heads, sc.counters + 2);
+      B_CUDA(cudaGetLastError());
+      uint32_t nheads = 0;
+      B_CUDA(cudaMemcpyAsync(&nheads, sc.counters + 2, 4, cudaMemcpyDeviceToHost, st));
+      B_CUDA(cudaStreamSynchronize(st));
+      k4<<<(nheads + 3) / 4, 128, smem4, st>>>(g, b, sc.req_key2, sc.perm2, sc.req_src, sc.req_d, nreq, sc.heads,
+                                               nheads);
+      B_CUDA(cudaGetLastError());
+    }
+    // a node above the current top becomes the entry point (hnsw.rs:206-218);
+    // the entry is the smallest id on the top layer (hnsw.rs:184-199)
+    for (uint32_t i = 0; i < bs; ++i) {
+      uint32_t id = inserted + i;
+      if (h->node_level[id] > g.top_level) {
+        g.top_level = h->node_level[id];
+        g.entry = id;
+      }
+    }
+    inserted += bs;
+  }
+  B_CUDA(cudaStreamSynchronize(st));
+#undef B_CUDA
+  hnsw_release_ws(h, ws);
+  h->n_levels = g.top_level + 1;
+  // the stored edge distances are only needed while building
+  cudaFree(h->d_adj0_dist);
+  h->d_adj0_dist = nullptr;
+  cudaFree(h->d_adj_up_dist);
+  h->d_adj_up_dist = nullptr;
+  *out = h;
+  return 0;
+}

@@ -1,0 +1,57 @@
+// hnsw_host.hpp — host-side state of a staged HNSW index (opaque cozo_gpu_hnsw_t).
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include "hnsw_device.cuh"
+
+struct HnswWorkspace {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  uint32_t* vis = nullptr;
+  size_t vis_words = 0;  // total words allocated
+  uint32_t* vlog = nullptr;
+  size_t vlog_words = 0;
+  uint32_t* counter = nullptr;
+  // staging buffers of the host-pointer API
+  float* q = nullptr;
+  size_t q_floats = 0;
+  uint32_t* ids = nullptr;
+  float* dist = nullptr;
+  uint32_t* count = nullptr;
+  uint32_t* qstats = nullptr;
+  size_t out_rows = 0, out_k = 0;
+  // pinned mirrors
+  float* h_q = nullptr;
+  size_t h_q_floats = 0;
+};
+
+struct cozo_gpu_hnsw {
+  cozo::HnswDev dev{};
+  // owned device buffers
+  float* d_vec = nullptr;
+  bool vec_owned = true;
+  uint32_t* d_adj0 = nullptr;
+  uint32_t* d_upper_off = nullptr;
+  uint32_t* d_adj_up = nullptr;
+  uint64_t up_rows = 0;
+  // builder-only companions (distances of the stored edges, hnsw.rs:281-318 `dist`)
+  float* d_adj0_dist = nullptr;
+  float* d_adj_up_dist = nullptr;
+  uint8_t* d_node_level = nullptr;
+  // host copies
+  std::vector<uint8_t> node_level;  // top layer index of each node (0 = layer 0 only)
+  uint32_t n_levels = 1;
+  uint32_t m_max0 = 0, m_max = 0;
+  std::mutex mu;
+  std::vector<HnswWorkspace*> pool;
+};
+
+namespace cozo {
+int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, uint32_t B, uint32_t k, uint32_t ef,
+                       double radius, uint32_t* d_ids, float* d_dist, uint32_t* d_count, uint32_t* d_qstats,
+                       cudaStream_t stream);
+HnswWorkspace* hnsw_acquire_ws(cozo_gpu_hnsw* h);
+void hnsw_release_ws(cozo_gpu_hnsw* h, HnswWorkspace* ws);
+int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words);
+}  // namespace cozo

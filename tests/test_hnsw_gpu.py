@@ -1,0 +1,232 @@
+"""GPU parity tests for the HNSW path: CUDA (through the C ABI) vs the CPU oracle on the
+same graph and the same seeded inputs.  Bar: identical top-k id sets up to distance
+near-ties (recall@k >= 0.999), distances within 1e-5 relative (f32 summation order differs
+from ndarray's 8-lane unrolled dot), identical traversal counters."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import uniform_vectors, recall, SEED_DATA, SEED_QUERY, SEED_LEVEL
+
+pytestmark = pytest.mark.gpu
+DIST_RTOL = 1e-5
+
+
+def _oracle_index(n, dim, m, efc, metric=O.L2, shift=0.0, seed=SEED_DATA):
+    X = uniform_vectors(n, dim, seed) - np.float32(shift)
+    ix = O.OracleHnsw.new(n, dim, metric=metric, m=m, ef_construction=efc, level_seed=SEED_LEVEL)
+    ix.insert_all(X)
+    return X, ix
+
+
+def _stage(gpu, X, lv, metric, m):
+    return gpu.HnswIndex.stage(X, lv.node_ids, lv.row_ptr, lv.col_idx, lv.entry, metric=metric, m_max0=2 * m, m_max=m)
+
+
+def _compare(gpu_out, orc_out, k, min_recall=0.999):
+    gi, gd, gc, gs = gpu_out
+    oi, od, oc, os_ = orc_out
+    assert np.array_equal(gc, oc)
+    r = recall(gi, oi)
+    assert r >= min_recall, f"recall {r}"
+    # distances: compare rank by rank (sorted lists)
+    fin = np.isfinite(od)
+    assert np.array_equal(np.isfinite(gd), fin)
+    assert np.allclose(gd[fin], od[fin], rtol=DIST_RTOL, atol=1e-6)
+    return r
+
+
+@pytest.fixture(scope="module")
+def cfg1(gpu):
+    """BASELINE config 1: 10k x 128 f32, m=16, ef_construction=200, ef=64, k=10, 1000 queries."""
+    X, ix = _oracle_index(10000, 128, 16, 200)
+    lv = ix.levels()
+    g = _stage(gpu, X, lv, gpu.L2, 16)
+    Q = uniform_vectors(1000, 128, SEED_QUERY)
+    return X, ix, g, Q
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_config1_parity(gpu, cfg1, mode):
+    X, ix, g, Q = cfg1
+    gpu.set_option("hnsw.mode", mode)
+    try:
+        gi, gd, gc, st = g.search(Q, 10, 64)
+    finally:
+        gpu.set_option("hnsw.mode", 1)
+    oi, od, oc, ost = ix.search(Q, 10, 64, n_threads=8)
+    _compare((gi, gd, gc, st), (oi, od, oc, ost), 10)
+    exact = np.mean([set(a) == set(b) for a, b in zip(gi, oi)])
+    assert exact >= 0.995
+    # identical traversal => identical counters, unless a distance near-tie flipped an admission
+    assert abs(int(st.dist_evals) - int(ost[:, 0].sum())) <= 0.001 * ost[:, 0].sum()
+    assert abs(int(st.nodes_expanded) - int(ost[:, 1].sum())) <= 0.001 * ost[:, 1].sum()
+    assert st.n_queries == 1000
+
+
+def test_roundtrip_export(gpu, cfg1):
+    X, ix, g, Q = cfg1
+    lv = ix.levels()
+    ni, rp, ci, ep = g.export_levels()
+    assert ep == lv.entry and len(rp) == lv.n_levels
+    for L in range(lv.n_levels):
+        assert np.array_equal(rp[L], lv.row_ptr[L]) and np.array_equal(ci[L], lv.col_idx[L])
+        if L:
+            assert np.array_equal(ni[L], lv.node_ids[L])
+
+
+def test_k_ef_radius_edges(gpu, cfg1):
+    X, ix, g, Q = cfg1
+    q = Q[:64]
+    for k, ef in [(1, 1), (1, 64), (10, 10), (100, 128), (200, 64), (3, 500)]:
+        out = g.search(q, k, ef)
+        ref = ix.search(q, k, ef, n_threads=8)
+        _compare(out, ref, k, min_recall=0.995)
+    ids, dist, cnt, _ = g.search(q, 10, 64)
+    r = float(np.median(dist[:, 5]))
+    out = g.search(q, 10, 64, radius=r)
+    ref = ix.search(q, 10, 64, radius=r, n_threads=8)
+    _compare(out, ref, 10, min_recall=0.995)
+    assert np.all(out[1][np.isfinite(out[1])] <= r)
+    assert np.all(out[0][np.arange(64)[:, None], np.arange(10)[None, :]][~np.isfinite(out[1])] == 0xFFFFFFFF)
+
+
+def test_self_query_is_nearest(gpu, cfg1):
+    X, ix, g, Q = cfg1
+    ids, dist, cnt, _ = g.search(X[:200], 1, 64)
+    assert np.mean(ids[:, 0] == np.arange(200)) > 0.97
+    hit = ids[:, 0] == np.arange(200)
+    assert np.all(dist[hit, 0] == 0.0)
+
+
+def test_argument_errors(gpu, cfg1):
+    X, ix, g, Q = cfg1
+    with pytest.raises(gpu.CozoGpuError) as e:
+        g.search(Q[:1], 0, 10)
+    assert e.value.code == gpu.E_INVAL           # k must be positive (program.rs normalize_hnsw)
+    with pytest.raises(gpu.CozoGpuError):
+        g.search(Q[:1], 10, 0)
+    ids, dist, cnt, st = g.search(np.zeros((0, 128), np.float32), 10, 64)
+    assert ids.shape == (0, 10) and st.n_queries == 0
+
+
+@pytest.mark.parametrize("metric,dim,shift", [(O.COSINE, 96, 0.5), (O.IP, 100, 0.5), (O.L2, 30, 0.0), (O.L2, 770, 0.0)])
+def test_metrics_and_ragged_dims(gpu, metric, dim, shift):
+    n = 3000 if dim < 500 else 1200
+    X, ix = _oracle_index(n, dim, 8, 60, metric=metric, shift=shift, seed=77 + dim)
+    g = _stage(gpu, X, ix.levels(), metric, 8)
+    Q = uniform_vectors(200, dim, 78) - np.float32(shift)
+    for mode in (0, 1):
+        gpu.set_option("hnsw.mode", mode)
+        try:
+            out = g.search(Q, 10, 80)
+        finally:
+            gpu.set_option("hnsw.mode", 1)
+        ref = ix.search(Q, 10, 80, n_threads=8)
+        _compare(out, ref, 10, min_recall=0.99)
+
+
+def test_empty_and_tiny_indexes(gpu):
+    X = uniform_vectors(5, 16, 1)
+    empty = O.OracleHnsw.new(5, 16, m=4, ef_construction=10)
+    lv = empty.levels()
+    g = _stage(gpu, X, lv, gpu.L2, 4)
+    ids, dist, cnt, _ = g.search(X, 3, 10)
+    assert np.all(cnt == 0) and np.all(ids == 0xFFFFFFFF)       # canary only (hnsw.rs:903-909)
+    one = O.OracleHnsw.new(5, 16, m=4, ef_construction=10)
+    one.insert(2, X[2])
+    g1 = _stage(gpu, X, one.levels(), gpu.L2, 4)
+    ids, dist, cnt, _ = g1.search(X, 3, 10)
+    assert np.all(cnt == 1) and np.all(ids[:, 0] == 2) and np.all(ids[:, 1:] == 0xFFFFFFFF)
+    full = O.OracleHnsw.new(5, 16, m=4, ef_construction=10)
+    full.insert_all(X)
+    g2 = _stage(gpu, X, full.levels(), gpu.L2, 4)
+    out = g2.search(X, 5, 10)
+    ref = full.search(X, 5, 10)
+    assert np.array_equal(out[0], ref[0])
+
+
+def test_stage_rejects_bad_input(gpu, cfg1):
+    X, ix, g, Q = cfg1
+    lv = ix.levels()
+    bad_ci = [c.copy() for c in lv.col_idx]
+    bad_ci[0][0] = 10_000_000
+    with pytest.raises(gpu.CozoGpuError) as e:
+        gpu.HnswIndex.stage(X, lv.node_ids, lv.row_ptr, bad_ci, lv.entry, m_max0=32, m_max=16)
+    assert e.value.code == gpu.E_INVAL
+
+
+def test_device_builder_parity_and_quality(gpu):
+    """The device builder yields a different (batched) graph than the sequential reference
+    insert; parity is GPU search == oracle search ON THE SAME exported graph, and the
+    graph must be a usable HNSW index (degree bounds, recall vs brute force)."""
+    n, dim, m = 20000, 64, 16
+    X = uniform_vectors(n, dim, 4242)
+    g = gpu.HnswIndex.build(X, m=m, ef_construction=100, level_seed=SEED_LEVEL)
+    ni, rp, ci, ep = g.export_levels()
+    deg0 = np.diff(rp[0].astype(np.int64))
+    assert deg0.max() <= 2 * m and deg0.min() >= 1
+    for L in range(1, len(rp)):
+        assert np.diff(rp[L].astype(np.int64)).max() <= m
+    assert ep == int(ni[-1].min()) if len(ni) > 1 else ep == 0
+    lv = O.HnswLevels(ni, rp, ci, ep)
+    ix = O.OracleHnsw.from_levels(X, lv)
+    Q = uniform_vectors(500, dim, 4243)
+    out = g.search(Q, 10, 100)
+    ref = ix.search(Q, 10, 100, n_threads=8)
+    _compare(out, ref, 10)
+    bi, _ = O.bruteforce_knn(X, Q, 10, n_threads=8)
+    assert recall(out[0], bi) > 0.9
+    # level populations follow the level law: about n / m on layer -1
+    if len(ni) > 1:
+        assert 0.5 * n / m < len(ni[1]) < 2.0 * n / m
+
+
+def test_builder_keep_pruned_and_cosine(gpu):
+    n, dim, m = 6000, 40, 8
+    X = uniform_vectors(n, dim, 555) - np.float32(0.5)
+    g = gpu.HnswIndex.build(X, metric=gpu.COSINE, m=m, ef_construction=60, keep_pruned_connections=True)
+    ni, rp, ci, ep = g.export_levels()
+    deg0 = np.diff(rp[0].astype(np.int64))
+    assert deg0.max() <= 2 * m
+    assert deg0.mean() > m          # back-fill keeps rows fuller than the plain heuristic
+    ix = O.OracleHnsw.from_levels(X, O.HnswLevels(ni, rp, ci, ep), metric=O.COSINE)
+    Q = uniform_vectors(200, dim, 556) - np.float32(0.5)
+    out = g.search(Q, 10, 80)
+    ref = ix.search(Q, 10, 80, n_threads=8)
+    _compare(out, ref, 10, min_recall=0.995)
+
+
+def test_search_dev_and_merge(gpu):
+    """device-pointer entry points + per-shard top-k merge against a numpy merge"""
+    import torch
+    n, dim, m, S, B, k = 8000, 32, 8, 4, 300, 10
+    X = uniform_vectors(n, dim, 999)
+    Q = uniform_vectors(B, dim, 998)
+    per = n // S
+    dq = torch.from_numpy(Q).cuda()
+    all_d = torch.empty((S, B, k), dtype=torch.float32, device="cuda")
+    all_i = torch.empty((S, B, k), dtype=torch.int32, device="cuda")
+    host_d, host_i = [], []
+    for s in range(S):
+        sh = gpu.HnswIndex.build(X[s * per:(s + 1) * per], m=m, ef_construction=60, level_seed=s)
+        stream = torch.cuda.current_stream().cuda_stream
+        sh.search_dev(dq.data_ptr(), B, k, 64, all_i[s].data_ptr(), all_d[s].data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        hi, hd, _, _ = sh.search(Q, k, 64)
+        assert np.array_equal(all_i[s].cpu().numpy().view(np.uint32), hi)
+        host_d.append(hd)
+        host_i.append(hi.astype(np.int64) + s * per)
+    offs = torch.tensor([s * per for s in range(S)], dtype=torch.int64, device="cuda")
+    out_i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    out_d = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    gpu.topk_merge_dev(all_d.data_ptr(), all_i.data_ptr(), S, B, k, offs.data_ptr(), out_i.data_ptr(), out_d.data_ptr(),
+                       stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    cd = np.concatenate(host_d, axis=1)
+    cid = np.concatenate(host_i, axis=1)
+    order = np.argsort(cd, axis=1, kind="stable")[:, :k]
+    exp_d = np.take_along_axis(cd, order, 1)
+    exp_i = np.take_along_axis(cid, order, 1)
+    assert np.array_equal(out_d.cpu().numpy(), exp_d)
+    assert np.mean(out_i.cpu().numpy() == exp_i) > 0.999

@@ -1,0 +1,273 @@
+"""CPU tests: the oracle against independent implementations and known answers.
+PARITY UNPINNED: the reference has no golden vectors for this path;
+these tests pin the oracle to closed-form values and to scipy / networkx / brute force."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import uniform_vectors, recall, rmat_edges, SEED_DATA, SEED_QUERY, SEED_LEVEL
+
+
+def test_distance_known_answers():
+    # sanity identities the reference asserts informally (runtime/tests.rs:693-694)
+    v = np.array([1, 2, 3, 4, 5, 6, 7, 8, 9], np.float32)
+    assert O.vec_dist(O.L2, v, v) == 0.0
+    assert abs(O.vec_dist(O.COSINE, v, v)) < 1e-7
+    n = v / np.sqrt(np.float32(np.dot(v, v)))
+    assert abs(O.vec_dist(O.IP, n, n)) < 1e-6
+    a = np.array([1, 0, 0], np.float32)
+    b = np.array([0, 1, 0], np.float32)
+    assert O.vec_dist(O.L2, a, b) == 2.0          # squared, no sqrt (hnsw.rs:70-71)
+    assert O.vec_dist(O.COSINE, a, b) == 1.0
+    assert O.vec_dist(O.IP, a, b) == 1.0
+    assert O.vec_dist(O.IP, a, a) == 0.0
+
+
+def test_unrolled_dot_order():
+    # ndarray 0.15.6 unrolled_dot: 8 accumulators, (p0+p4)+(p1+p5)+(p2+p6)+(p3+p7), then tail
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(27).astype(np.float32)
+    y = rng.standard_normal(27).astype(np.float32)
+    p = np.zeros(8, np.float32)
+    for j in range(3):
+        for i in range(8):
+            p[i] = np.float32(p[i] + np.float32(x[8 * j + i] * y[8 * j + i]))
+    s = np.float32(0)
+    for i in range(4):
+        s = np.float32(s + np.float32(p[i] + p[i + 4]))
+    for i in range(24, 27):
+        s = np.float32(s + np.float32(x[i] * y[i]))
+    assert O.vec_dist(O.IP, x, y) == 1.0 - float(s)
+
+
+@pytest.fixture(scope="module")
+def small_index():
+    X = uniform_vectors(3000, 48, SEED_DATA)
+    ix = O.OracleHnsw.new(3000, 48, m=12, ef_construction=80, level_seed=SEED_LEVEL)
+    ix.insert_all(X)
+    return X, ix
+
+
+def test_hnsw_structure(small_index):
+    X, ix = small_index
+    lv = ix.levels()
+    assert lv.n_levels >= 2
+    deg0 = np.diff(lv.row_ptr[0])
+    assert deg0.max() <= 24 and deg0.min() >= 1           # m_max0 = 2m (relation.rs:1146)
+    for L in range(1, lv.n_levels):
+        assert np.diff(lv.row_ptr[L]).max() <= 12          # m_max = m
+        assert np.all(np.diff(lv.node_ids[L].astype(np.int64)) > 0)
+        # every node of layer -L is on layer -(L-1)
+        lower = set(range(3000)) if L == 1 else set(lv.node_ids[L - 1].tolist())
+        assert set(lv.node_ids[L].tolist()) <= lower
+    # entry = smallest id on the top layer (first row in key order, hnsw.rs:891-899)
+    assert lv.entry == int(lv.node_ids[-1].min())
+    # no self loops, targets sorted (key order)
+    rp, ci = lv.row_ptr[0], lv.col_idx[0]
+    for i in range(0, 3000, 97):
+        row = ci[rp[i]:rp[i + 1]]
+        assert i not in row and np.all(np.diff(row.astype(np.int64)) > 0)
+
+
+def test_hnsw_search_vs_bruteforce(small_index):
+    X, ix = small_index
+    Q = uniform_vectors(100, 48, SEED_QUERY)
+    ids, dist, cnt, st = ix.search(Q, 10, 100)
+    bi, bd = O.bruteforce_knn(X, Q, 10)
+    assert recall(ids, bi) > 0.9
+    assert np.all(cnt == 10)
+    assert np.all(np.diff(dist, axis=1) >= 0)              # nearest first (hnsw.rs:1005)
+    for i in range(0, 100, 7):                              # reported distances are the true ones
+        for j in range(10):
+            assert dist[i, j] == O.vec_dist(O.L2, Q[i], X[ids[i, j]])
+    assert np.all(st[:, 0] >= st[:, 1]) and np.all(st[:, 1] >= 1)
+
+
+def test_hnsw_radius_and_k(small_index):
+    X, ix = small_index
+    Q = uniform_vectors(8, 48, 99)
+    ids, dist, cnt, _ = ix.search(Q, 10, 64)
+    r = float(dist[:, 4].max())
+    ids2, dist2, cnt2, _ = ix.search(Q, 10, 64, radius=r)
+    for i in range(8):
+        keep = dist[i] <= r
+        assert cnt2[i] == keep.sum()
+        assert np.array_equal(ids2[i, :cnt2[i]], ids[i][keep])
+        assert np.all(ids2[i, cnt2[i]:] == 0xFFFFFFFF)
+    ids3, _, cnt3, _ = ix.search(Q, 3, 64)
+    assert np.array_equal(ids3, ids[:, :3]) and np.all(cnt3 == 3)
+
+
+def test_hnsw_view_roundtrip_and_empty(small_index):
+    X, ix = small_index
+    Q = uniform_vectors(20, 48, 5)
+    a = ix.search(Q, 5, 40)
+    ix2 = O.OracleHnsw.from_levels(X, ix.levels())
+    b = ix2.search(Q, 5, 40)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+    empty = O.OracleHnsw.new(10, 48)
+    ids, dist, cnt, _ = empty.search(Q, 5, 40)
+    assert np.all(cnt == 0) and np.all(ids == 0xFFFFFFFF)  # canary only (hnsw.rs:903-909)
+
+
+def test_hnsw_remove_and_reinsert():
+    X = uniform_vectors(400, 16, 11)
+    ix = O.OracleHnsw.new(400, 16, m=6, ef_construction=40)
+    ix.insert_all(X)
+    for i in range(0, 400, 3):
+        ix.remove(i)
+    lv = ix.levels()
+    gone = set(range(0, 400, 3))
+    assert not (set(lv.col_idx[0].tolist()) & gone)
+    Q = uniform_vectors(10, 16, 12)
+    ids, _, cnt, _ = ix.search(Q, 5, 50)
+    assert not (set(ids.ravel().tolist()) & gone)
+    ix.insert(0, X[0])
+    ids, dist, _, _ = ix.search(X[0:1], 1, 50)
+    assert ids[0, 0] == 0 and dist[0, 0] == 0.0
+
+
+def test_cosine_and_ip_indexes():
+    X = uniform_vectors(1500, 24, 21) - 0.5
+    Q = uniform_vectors(40, 24, 22) - 0.5
+    for metric in (O.COSINE, O.IP):
+        ix = O.OracleHnsw.new(1500, 24, metric=metric, m=10, ef_construction=60)
+        ix.insert_all(X)
+        ids, _, _, _ = ix.search(Q, 10, 120)
+        bi, _ = O.bruteforce_knn(X, Q, 10, metric=metric)
+        assert recall(ids, bi) > 0.8
+
+
+# ---------------------------------------------------------------- graphs ---
+def _random_graph(n, m, seed, weighted=True):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, n, m).astype(np.uint32)
+    dst = rng.integers(0, n, m).astype(np.uint32)
+    w = (rng.integers(1, 64, m) / 8.0).astype(np.float32) if weighted else None   # exact in f32
+    return src, dst, w
+
+
+def test_csr_layout():
+    src = np.array([2, 0, 0, 2, 1, 0], np.uint32)
+    dst = np.array([1, 2, 1, 0, 2, 1], np.uint32)
+    w = np.array([5, 1, 2, 3, 4, 9], np.float32)
+    g = O.OracleGraph(3, src, dst, w)
+    op, oi, ow, ip, ii = g.export()
+    assert op.tolist() == [0, 3, 4, 6] and oi.tolist() == [1, 1, 2, 2, 0, 1]   # sorted targets, parallel edge kept
+    assert ow.tolist() == [2, 9, 1, 4, 3, 5]
+    assert ip.tolist() == [0, 1, 4, 6] and ii.tolist() == [2, 0, 0, 2, 0, 1]
+
+
+def test_pagerank_hand_graph():
+    # 0->1, 0->2, 1->2, 2->0, 3->2 ; node 3 has no in-edges
+    src = np.array([0, 0, 1, 2, 3], np.uint32)
+    dst = np.array([1, 2, 2, 0, 2], np.uint32)
+    g = O.OracleGraph(4, src, dst)
+    s, it, err = g.pagerank(damping=0.85, tol=0.0, max_iter=1)
+    init, base = 0.25, 0.15 / 4
+    exp = [base + 0.85 * init, base + 0.85 * init / 2, base + 0.85 * (init / 2 + init + init), base]
+    assert it == 1 and np.allclose(s, exp, rtol=1e-6)
+    # no dangling redistribution / renormalisation: mass is not conserved in general
+    s, it, err = g.pagerank(tol=1e-12, max_iter=200)
+    s2, it2, _ = g.pagerank(tol=1e-12, max_iter=200, variant="gs")
+    assert np.allclose(s, s2, rtol=2e-6)
+
+
+def test_pagerank_dangling_node():
+    # node 2 is dangling: its contribution is inf/unused, never read
+    src = np.array([0, 1], np.uint32)
+    dst = np.array([1, 2], np.uint32)
+    g = O.OracleGraph(3, src, dst)
+    s, it, _ = g.pagerank(tol=0.0, max_iter=3)
+    assert np.all(np.isfinite(s)) and it == 3
+    assert abs(s.sum() - 1.0) > 1e-3     # documents the "no redistribution" behaviour
+
+
+def test_pagerank_stops_on_epsilon():
+    src, dst, _ = _random_graph(200, 2000, 5, weighted=False)
+    g = O.OracleGraph(200, src, dst)
+    s, it, err = g.pagerank(tol=1e-4, max_iter=100)
+    assert it < 100 and err < float(np.float32(1e-4))
+    s, it, err = g.pagerank(tol=1e-4, max_iter=3)
+    assert it == 3
+
+
+def test_dijkstra_vs_scipy():
+    import scipy.sparse as sp
+    import scipy.sparse.csgraph as cg
+    n = 300
+    src, dst, w = _random_graph(n, 1500, 7)
+    g = O.OracleGraph(n, src, dst, w)
+    sources = np.arange(0, n, 13, dtype=np.uint32)
+    dist, back = g.sssp(sources, n_threads=4)
+    A = {}
+    for s, t, ww in zip(src, dst, w):
+        A[(int(s), int(t))] = min(A.get((int(s), int(t)), 1e30), float(ww))
+    S = sp.csr_matrix((list(A.values()), ([k[0] for k in A], [k[1] for k in A])), shape=(n, n))
+    ref = cg.dijkstra(S, indices=sources)
+    assert np.array_equal(np.isfinite(ref), np.isfinite(dist))
+    fin = np.isfinite(ref)
+    assert np.array_equal(dist[fin], ref[fin].astype(np.float32))   # weights are dyadic: sums exact
+    # back pointers give a path of that cost
+    for si, s in enumerate(sources):
+        for t in range(0, n, 17):
+            if not np.isfinite(dist[si, t]) or t == s:
+                continue
+            cost, cur, hops = 0.0, t, 0
+            while cur != s:
+                p = int(back[si, cur])
+                cost += A[(p, cur)]
+                cur = p
+                hops += 1
+                assert hops <= n
+            assert cost == dist[si, t]
+
+
+def test_dijkstra_goals_stop_early():
+    n = 200
+    src, dst, w = _random_graph(n, 1200, 8)
+    g = O.OracleGraph(n, src, dst, w)
+    full, _ = g.sssp([0])
+    goals = np.array([5, 9], np.uint32)
+    part, _ = g.sssp([0], goals=goals)
+    assert np.array_equal(part[0, goals], full[0, goals])
+
+
+def test_keep_ties_predecessors():
+    # diamond: 0->1->3, 0->2->3 with equal cost, plus a longer 0->3
+    src = np.array([0, 0, 1, 2, 0], np.uint32)
+    dst = np.array([1, 2, 3, 3, 3], np.uint32)
+    w = np.array([1, 1, 1, 1, 5], np.float32)
+    g = O.OracleGraph(4, src, dst, w)
+    dist, bp, bi = g.sssp_keep_ties(0)
+    assert dist.tolist() == [0, 1, 1, 2]
+    assert sorted(bi[bp[3]:bp[4]].tolist()) == [1, 2]
+
+
+def test_closeness_and_betweenness_vs_networkx():
+    import networkx as nx
+    n = 120
+    src, dst, w = _random_graph(n, 700, 9)
+    g = O.OracleGraph(n, src, dst, w)
+    A = {}
+    for s, t, ww in zip(src, dst, w):
+        A[(int(s), int(t))] = min(A.get((int(s), int(t)), 1e30), float(ww))
+    G = nx.DiGraph()
+    G.add_nodes_from(range(n))
+    for (a, b), ww in A.items():
+        G.add_edge(a, b, weight=ww)
+    bt = g.betweenness(n_threads=4)
+    nb = nx.betweenness_centrality(G, normalized=False, weight="weight")
+    assert np.allclose(bt, [nb[i] for i in range(n)], rtol=1e-5, atol=1e-5)
+    cl = g.closeness(n_threads=4)
+    lengths = dict(nx.all_pairs_dijkstra_path_length(G, weight="weight"))
+    for u in range(0, n, 5):
+        d = lengths[u]
+        nc, tot = len(d), sum(d.values())     # nc counts u itself (d(u,u)=0), all_pairs_shortest_path.rs:118-120
+        exp = np.inf if tot == 0 else nc * nc / tot / (n - 1)
+        assert np.isclose(cl[u], exp, rtol=1e-5) or (np.isinf(exp) and np.isinf(cl[u]))
+
+
+def test_rmat_generator_shape():
+    n, s, d = rmat_edges(10, 16, 0x5EED0004)
+    assert n == 1024 and s.size == 16384 and s.max() < n and d.max() < n
