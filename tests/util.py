@@ -14,8 +14,7 @@ def recall(a_ids, b_ids):
     for x, y in zip(a_ids, b_ids):
         sx = set(int(v) for v in x if v != 0xFFFFFFFF)
         sy = set(int(v) for v in y if v != 0xFFFFFFFF)
-        denom = max(len(sy), 1)
-        tot += len(sx & sy) / denom
+        tot += 1.0 if not sy else len(sx & sy) / len(sy)
     return tot / len(a_ids)
 
 
