@@ -224,21 +224,17 @@ def main():
     dd = torch.empty((B, k), dtype=torch.float32, device=dev)
     qstats = torch.zeros((nsteps, B, 4), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    sharded = None
     if world > 1:
         import torch.distributed as dist
-        all_d = torch.empty((world, B, k), dtype=torch.float32, device=dev)
-        all_i = torch.empty((world, B, k), dtype=torch.int32, device=dev)
-        offs = torch.tensor([r * a.n for r in range(world)], dtype=torch.int64, device=dev)
-        out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
-        out_d = torch.empty((B, k), dtype=torch.float32, device=dev)
+        from cozo_b200.sharded import ShardedHnswSearch
+        sharded = ShardedHnswSearch(g, a.n, dev)
 
     def step(s):
-        g.search_dev(Qd[s].data_ptr(), B, k, ef, ids.data_ptr(), dd.data_ptr(), None, qstats[s].data_ptr(), stream)
-        if world > 1:
-            dist.all_gather_into_tensor(all_d.view(-1), dd.view(-1))
-            dist.all_gather_into_tensor(all_i.view(-1), ids.view(-1))
-            capi.topk_merge_dev(all_d.data_ptr(), all_i.data_ptr(), world, B, k, offs.data_ptr(), out_i.data_ptr(),
-                                out_d.data_ptr(), stream)
+        if sharded is None:
+            g.search_dev(Qd[s].data_ptr(), B, k, ef, ids.data_ptr(), dd.data_ptr(), None, qstats[s].data_ptr(), stream)
+        else:   # local search -> ONE all-gather per list -> merge kernel
+            sharded.search(Qd[s], k, ef, qstats[s])
 
     for s in range(a.warmup):
         step(s)
@@ -307,12 +303,13 @@ def main():
         hi, hd, hc, hst = g.search(hq[s].numpy(), k, ef)
         if world > 1:
             # host-API path of the sharded operator: per-shard lists -> device -> all-gather -> merge -> host
-            dd.copy_(torch.from_numpy(hd))
-            ids.copy_(torch.from_numpy(hi.view(np.int32)))
-            dist.all_gather_into_tensor(all_d.view(-1), dd.view(-1))
-            dist.all_gather_into_tensor(all_i.view(-1), ids.view(-1))
-            capi.topk_merge_dev(all_d.data_ptr(), all_i.data_ptr(), world, B, k, offs.data_ptr(), out_i.data_ptr(),
-                                out_d.data_ptr(), stream)
+            ld = torch.from_numpy(hd).to(dev)
+            li = torch.from_numpy(hi.view(np.int32)).to(dev)
+            all_d, all_i = sharded.plumb.gather(ld, li)
+            out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+            out_d = torch.empty((B, k), dtype=torch.float32, device=dev)
+            capi.topk_merge_dev(all_d.data_ptr(), all_i.data_ptr(), world, B, k, sharded.plumb.offsets.data_ptr(),
+                                out_i.data_ptr(), out_d.data_ptr(), stream)
             _ = out_i.cpu()
         dt = time.perf_counter() - t0
         if s >= a.warmup:
@@ -334,7 +331,6 @@ def main():
         sample = min(a.cpu_sample, B)
         s_last = a.warmup + a.steps - 1
         qps, oids, ost = cpu_oracle_qps(X, levels, Qh[s_last][:sample], k, ef, cores)
-        gi = ids.cpu().numpy().view(np.uint32)[:sample] if False else None
         hi, hd, _, _ = g.search(Qh[s_last][:sample], k, ef)
         recall_vs_oracle = float(np.mean([len(set(x) & set(y)) / k for x, y in zip(hi, oids)]))
         cpu_baseline = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",

@@ -71,5 +71,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_host(force: bool = False) -> str:
+    """pybind11 harness over the C++ host layer (cozo_b200/host/*.hpp), linked against libcozo_gpu.so."""
+    import sysconfig
+    import pybind11
+    host = os.path.join(HERE, "host")
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    out = os.path.join(host, "_cozo_host" + ext)
+    deps = [os.path.join(host, f) for f in ("pymod.cpp", "data_value.hpp", "fixed_rule.hpp", "hnsw.hpp")]
+    deps.append(os.path.join(CSRC, "..", "..", "include", "cozo_gpu.h"))
+    if force or _stale(out, deps) or _stale(out, [OUT]):
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
+               "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+               os.path.join(host, "pymod.cpp"), "-o", out,
+               "-L", CSRC, "-lcozo_gpu", "-Wl,-rpath,$ORIGIN/../csrc"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"host module build failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

@@ -1,0 +1,315 @@
+// hnsw.hpp — host side of the HNSW operator: staging the index *relation* into the
+// device layout, SessionTx::hnsw_knn's row assembly, and the HnswSearchRA operator that
+// collects parent tuples, launches one batched search and scatters the results.
+//
+// Mirrors (same names / argument meaning / error behaviour):
+//   HnswIndexManifest                    runtime/hnsw.rs:27-43, runtime/relation.rs:1136-1151
+//   index relation schema                runtime/relation.rs:1064-1126
+//   hnsw_get_neighbours reading rules    runtime/hnsw.rs:588-629
+//   SessionTx::hnsw_knn                  runtime/hnsw.rs:869-1012
+//   HnswSearch / all_bindings            data/program.rs:976-991, 1016-1025
+//   HnswSearchRA::iter                   query/ra.rs:1085-1121
+#pragma once
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <optional>
+
+#include "fixed_rule.hpp"
+
+namespace cozo_host {
+
+enum class HnswDistance { L2 = COZO_GPU_L2, Cosine = COZO_GPU_COSINE, InnerProduct = COZO_GPU_IP };  // sys.rs:94-98
+
+struct HnswIndexManifest {  // hnsw.rs:27-43
+  std::string base_relation, index_name;
+  size_t vec_dim = 0;
+  bool dtype_f64 = false;          // VecElementType::F64 is outside the device envelope
+  std::vector<size_t> vec_fields;  // column indices of the base relation holding vectors
+  HnswDistance distance = HnswDistance::L2;
+  size_t ef_construction = 0, m_neighbours = 0, m_max = 0, m_max0 = 0;
+  double level_multiplier = 0;
+  bool extend_candidates = false, keep_pruned_connections = false;
+  // relation.rs:1145-1147
+  void derive() {
+    m_max = m_neighbours;
+    m_max0 = m_neighbours * 2;
+    level_multiplier = 1.0 / std::log((double)m_neighbours);
+  }
+};
+
+// A stored relation as the operator sees it: key columns then value columns, rows in key order.
+struct RelationHandle {
+  std::string name;
+  std::vector<std::string> keys, non_keys;  // column names
+  std::map<Tuple, Tuple, TupleLess> rows;   // key tuple -> full row (keys ++ values)
+  void put(const Tuple& full) {
+    Tuple k(full.begin(), full.begin() + keys.size());
+    rows[k] = full;
+  }
+  const Tuple* get(const Tuple& key) const {
+    auto it = rows.find(key);
+    return it == rows.end() ? nullptr : &it->second;
+  }
+};
+
+using CompoundKey = std::tuple<Tuple, size_t, int32_t>;  // hnsw.rs:55
+struct CompoundKeyLess {
+  bool operator()(const CompoundKey& a, const CompoundKey& b) const {
+    int c = cmp_tuple(std::get<0>(a), std::get<0>(b));
+    if (c) return c < 0;
+    if (std::get<1>(a) != std::get<1>(b)) return std::get<1>(a) < std::get<1>(b);
+    return std::get<2>(a) < std::get<2>(b);
+  }
+};
+
+// The device-resident copy of one index: a cache of the index relation.
+struct StagedHnswIndex {
+  cozo_gpu_hnsw_t* h = nullptr;
+  std::vector<CompoundKey> keys;  // dense id -> compound key (key order)
+  HnswIndexManifest manifest;
+  uint64_t n_edges_kept = 0, n_rows_dropped_same_key = 0, n_rows_dropped_ignored = 0;
+  StagedHnswIndex() = default;
+  StagedHnswIndex(const StagedHnswIndex&) = delete;
+  StagedHnswIndex& operator=(const StagedHnswIndex&) = delete;
+  ~StagedHnswIndex() {
+    if (h) cozo_gpu_hnsw_free(h);
+  }
+
+  // idx_rows: scan_all of the index relation, i.e. tuples
+  //   (layer, fr_k.., fr__field, fr__sub_idx, to_k.., to__field, to__sub_idx, dist, hash, ignore_link)
+  // in key order (relation.rs:1064-1126).  K = number of key columns of the base relation.
+  void stage(const RelationHandle& base, std::vector<Tuple> idx_rows, const HnswIndexManifest& mf) {
+    manifest = mf;
+    if (mf.dtype_f64)
+      throw CozoError("gpu::unsupported", "F64 vector indexes are outside the device envelope (f32 only)");
+    const size_t K = base.keys.size();
+    std::sort(idx_rows.begin(), idx_rows.end(), TupleLess());
+    // dense ids = compound keys of the layer-0 self-loop rows, in key order
+    std::map<CompoundKey, uint32_t, CompoundKeyLess> ids;
+    auto fr_key = [&](const Tuple& t, bool& canary) -> CompoundKey {
+      int64_t fld = 0, sub = 0;
+      canary = !t[K + 1].get_int(fld);  // canary row: fr__field is Null (hnsw.rs:903-909)
+      if (!canary) t[K + 2].get_int(sub);
+      return CompoundKey(Tuple(t.begin() + 1, t.begin() + 1 + K), (size_t)fld, (int32_t)sub);
+    };
+    auto to_key = [&](const Tuple& t) -> CompoundKey {
+      int64_t fld = 0, sub = 0;
+      t[2 * K + 3].get_int(fld);
+      t[2 * K + 4].get_int(sub);
+      return CompoundKey(Tuple(t.begin() + K + 3, t.begin() + 2 * K + 3), (size_t)fld, (int32_t)sub);
+    };
+    for (const Tuple& t : idx_rows) {
+      if (t.size() != 2 * K + 8) throw CozoError("", "corrupted index: bad row width");
+      int64_t layer;
+      if (!t[0].get_int(layer) || layer != 0) continue;
+      bool canary;
+      CompoundKey f = fr_key(t, canary);
+      if (canary) continue;
+      ids.emplace(f, 0u);
+    }
+    keys.clear();
+    for (auto& kv : ids) {
+      kv.second = (uint32_t)keys.size();
+      keys.push_back(kv.first);
+    }
+    const uint32_t n = (uint32_t)keys.size();
+    // entry point: the first row in key order with layer in [i64::MIN, 1] (hnsw.rs:891-899)
+    uint32_t entry = COZO_GPU_NONE;
+    int64_t bottom_level = 0;
+    for (const Tuple& t : idx_rows) {
+      int64_t layer;
+      if (!t[0].get_int(layer) || layer > 1) continue;
+      bool canary;
+      CompoundKey f = fr_key(t, canary);
+      if (!canary) {
+        bottom_level = layer;
+        auto it = ids.find(f);
+        if (it == ids.end()) throw CozoError("", "corrupted index");
+        entry = it->second;
+      }
+      break;
+    }
+    const uint32_t n_levels = entry == COZO_GPU_NONE ? 1 : (uint32_t)(-bottom_level) + 1;
+    // adjacency with the reading rules of hnsw_get_neighbours(include_deleted=false)
+    std::vector<std::vector<uint32_t>> node_ids(n_levels);
+    std::vector<std::map<uint32_t, std::vector<uint32_t>>> adj(n_levels);
+    for (const Tuple& t : idx_rows) {
+      int64_t layer;
+      if (!t[0].get_int(layer) || layer > 0) continue;
+      bool canary;
+      CompoundKey f = fr_key(t, canary);
+      if (canary) continue;
+      const uint32_t L = (uint32_t)(-layer);
+      if (L >= n_levels) continue;
+      CompoundKey to = to_key(t);
+      uint32_t fi = ids.at(f);
+      auto& row = adj[L][fi];  // self-loop rows create the (possibly empty) row
+      if (cmp_tuple(std::get<0>(to), std::get<0>(f)) == 0) {  // hnsw.rs:609: tuple key only
+        n_rows_dropped_same_key++;
+        continue;
+      }
+      bool ignored = false;
+      t[2 * K + 7].get_bool(ignored);
+      if (ignored) {  // hnsw.rs:618-620
+        n_rows_dropped_ignored++;
+        continue;
+      }
+      auto it = ids.find(to);
+      if (it == ids.end()) throw CozoError("", "corrupted index: edge to an unknown vector");
+      row.push_back(it->second);  // rows arrive in key order => ascending ids
+      n_edges_kept++;
+    }
+    // vectors (VectorCache::ensure_key, hnsw.rs:122-151)
+    std::vector<float> vectors((size_t)n * mf.vec_dim);
+    for (uint32_t i = 0; i < n; ++i) {
+      const Tuple* row = base.get(std::get<0>(keys[i]));
+      if (!row) throw CozoError("", "Cannot find compound key for HNSW");
+      const DataValue* field = &(*row)[std::get<1>(keys[i])];
+      if (std::get<2>(keys[i]) >= 0) {
+        if (field->kind != DataValue::List) throw CozoError("", "Cannot interpret " + field->repr() + " as list");
+        field = &field->list[(size_t)std::get<2>(keys[i])];
+      }
+      if (field->kind != DataValue::Vec || field->v->size() != mf.vec_dim)
+        throw CozoError("", "Cannot interpret " + field->repr() + " as vector");
+      std::copy(field->v->begin(), field->v->end(), vectors.begin() + (size_t)i * mf.vec_dim);
+    }
+    // flatten to the C ABI descriptor
+    std::vector<CozoGpuHnswLevel> levels(n_levels);
+    std::vector<std::vector<uint64_t>> row_ptr(n_levels);
+    std::vector<std::vector<uint32_t>> col_idx(n_levels);
+    for (uint32_t L = 0; L < n_levels; ++L) {
+      row_ptr[L].push_back(0);
+      if (L == 0) {
+        for (uint32_t i = 0; i < n; ++i) {
+          auto it = adj[0].find(i);
+          if (it != adj[0].end()) col_idx[0].insert(col_idx[0].end(), it->second.begin(), it->second.end());
+          row_ptr[0].push_back(col_idx[0].size());
+        }
+      } else {
+        for (auto& kv : adj[L]) {
+          node_ids[L].push_back(kv.first);
+          col_idx[L].insert(col_idx[L].end(), kv.second.begin(), kv.second.end());
+          row_ptr[L].push_back(col_idx[L].size());
+        }
+      }
+      levels[L].n_nodes = L == 0 ? n : (uint32_t)node_ids[L].size();
+      levels[L].node_ids = L == 0 ? nullptr : node_ids[L].data();
+      levels[L].row_ptr = row_ptr[L].data();
+      levels[L].col_idx = col_idx[L].data();
+    }
+    CozoGpuHnswStageDesc d{};
+    d.n_vectors = n;
+    d.dim = (uint32_t)mf.vec_dim;
+    d.metric = (int32_t)mf.distance;
+    d.n_levels = n_levels;
+    d.levels = levels.data();
+    d.vectors = vectors.data();
+    d.vectors_on_device = 0;
+    d.entry_point = entry;
+    d.m_max0 = (uint32_t)mf.m_max0;
+    d.m_max = (uint32_t)mf.m_max;
+    if (h) {
+      cozo_gpu_hnsw_free(h);
+      h = nullptr;
+    }
+    gpu_check(cozo_gpu_hnsw_stage(&h, &d));
+  }
+};
+
+// HnswSearch (data/program.rs:976-991): the operator's parameter block
+struct HnswSearch {
+  const RelationHandle* base_handle = nullptr;
+  const StagedHnswIndex* index = nullptr;  // stands for idx_handle + manifest
+  size_t k = 0, ef = 0;
+  bool bind_field = false, bind_field_idx = false, bind_distance = false, bind_vector = false;
+  std::optional<double> radius;
+  std::function<bool(const Tuple&)> filter;  // compiled filter bytecode stand-in (hnsw.rs:997-1001)
+
+  void validate() const {  // SearchInput::normalize_hnsw (program.rs:1341-1569)
+    if (k == 0) throw CozoError("parser::expected_positive_int_for_hnsw_k", "Expected positive integer for `k`");
+    if (ef == 0) throw CozoError("parser::expected_positive_int_for_hnsw_ef", "Expected positive integer for `ef`");
+    if (radius && !(*radius > 0.))
+      throw CozoError("parser::expected_positive_float_for_hnsw_radius", "Expected positive float for `radius`");
+  }
+};
+
+// SessionTx::hnsw_knn for a whole batch of query vectors (hnsw.rs:869-1012).
+// Returns, per query, the rows `base row ++ [field name] ++ [field idx] ++ [distance] ++ [vector]`.
+inline std::vector<std::vector<Tuple>> hnsw_knn_batch(const std::vector<const std::vector<float>*>& queries,
+                                                      const HnswSearch& config, CozoGpuSearchStats* stats = nullptr) {
+  const StagedHnswIndex& ix = *config.index;
+  const size_t dim = ix.manifest.vec_dim;
+  const uint32_t B = (uint32_t)queries.size();
+  std::vector<float> q((size_t)B * dim);
+  for (uint32_t i = 0; i < B; ++i) {
+    if (queries[i]->size() != dim) throw CozoError("", "query vector dimension mismatch");  // hnsw.rs:876-878
+    std::copy(queries[i]->begin(), queries[i]->end(), q.begin() + (size_t)i * dim);
+  }
+  // with a filter the trim to k happens after filtering (hnsw.rs:943-947, 1005-1006)
+  const uint32_t k_dev = config.filter ? (uint32_t)config.ef : (uint32_t)std::min(config.k, config.ef);
+  std::vector<uint32_t> ids((size_t)B * k_dev), count(B);
+  std::vector<float> dist((size_t)B * k_dev);
+  gpu_check(cozo_gpu_hnsw_search(ix.h, q.data(), B, k_dev, (uint32_t)config.ef, config.radius ? *config.radius : -1.0,
+                                 ids.data(), dist.data(), count.data(), stats));
+  const RelationHandle& base = *config.base_handle;
+  std::vector<std::vector<Tuple>> out(B);
+  for (uint32_t i = 0; i < B; ++i) {
+    for (uint32_t j = 0; j < count[i]; ++j) {
+      const CompoundKey& ck = ix.keys[ids[(size_t)i * k_dev + j]];
+      const Tuple* row = base.get(std::get<0>(ck));
+      if (!row) throw CozoError("", "corrupted index");  // hnsw.rs:958-961
+      Tuple cand = *row;
+      const size_t fld = std::get<1>(ck);
+      const int32_t sub = std::get<2>(ck);
+      if (config.bind_field)  // hnsw.rs:964-974
+        cand.push_back(DataValue::from_str(fld < base.keys.size() ? base.keys[fld] : base.non_keys[fld - base.keys.size()]));
+      if (config.bind_field_idx) cand.push_back(sub < 0 ? DataValue::null() : DataValue::from_int(sub));  // 975-981
+      if (config.bind_distance) cand.push_back(DataValue::from_float((double)dist[(size_t)i * k_dev + j]));  // 982-984
+      if (config.bind_vector) {  // 985-995
+        if (sub < 0) {
+          cand.push_back((*row)[fld]);
+        } else {
+          if ((*row)[fld].kind != DataValue::List) throw CozoError("", "corrupted index value");
+          cand.push_back((*row)[fld].list[(size_t)sub]);
+        }
+      }
+      if (config.filter && !config.filter(cand)) continue;  // hnsw.rs:997-1001
+      out[i].push_back(std::move(cand));
+    }
+    if (out[i].size() > config.k) out[i].resize(config.k);  // hnsw.rs:1006
+  }
+  return out;
+}
+
+// HnswSearchRA (query/ra.rs:896-901, 1085-1121): for every parent tuple, bind the query
+// column, search, emit parent ++ result.  The reference does this lazily one tuple at a
+// time; the operator is a pure function of (tuple, index snapshot), so draining the parent
+// into ONE batched launch and re-emitting in parent order is equivalent.
+struct HnswSearchRA {
+  HnswSearch hnsw_search;
+  size_t bind_idx = 0;  // position of the `query` variable in the parent bindings (ra.rs:1091-1098)
+  CozoGpuSearchStats last_stats{};
+
+  std::vector<Tuple> iter(const std::vector<Tuple>& parent) {
+    hnsw_search.validate();
+    std::vector<const std::vector<float>*> qs;
+    std::vector<std::shared_ptr<std::vector<float>>> keep;
+    for (const Tuple& t : parent) {
+      const DataValue& d = t.at(bind_idx);
+      if (d.kind != DataValue::Vec) throw CozoError("", "Expected vector, got " + d.repr());  // ra.rs:1106-1109
+      qs.push_back(d.v.get());
+    }
+    auto res = hnsw_knn_batch(qs, hnsw_search, &last_stats);
+    std::vector<Tuple> out;
+    for (size_t i = 0; i < parent.size(); ++i)
+      for (auto& r : res[i]) {  // ra.rs:1112-1116
+        Tuple row = parent[i];
+        row.insert(row.end(), r.begin(), r.end());
+        out.push_back(std::move(row));
+      }
+    return out;
+  }
+};
+
+}  // namespace cozo_host

@@ -1,0 +1,215 @@
+// pymod.cpp — pybind11 test harness over the C++ host layer (fixed_rule.hpp, hnsw.hpp).
+// It only converts Python objects to DataValues and back; all logic lives in the headers.
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "hnsw.hpp"
+
+namespace py = pybind11;
+using namespace cozo_host;
+
+static DataValue to_dv(const py::handle& o) {
+  if (o.is_none()) return DataValue::null();
+  if (py::isinstance<py::bool_>(o)) return DataValue::from_bool(o.cast<bool>());
+  if (py::isinstance<py::int_>(o)) return DataValue::from_int(o.cast<int64_t>());
+  if (py::isinstance<py::float_>(o)) return DataValue::from_float(o.cast<double>());
+  if (py::isinstance<py::str>(o)) return DataValue::from_str(o.cast<std::string>());
+  if (py::isinstance<py::bytes>(o)) return DataValue::from_bytes(o.cast<std::string>());
+  if (py::isinstance<py::array>(o)) {
+    // Vector::F32, or Vector::F64 cast to the index dtype (hnsw.rs:879-884)
+    auto a = py::array_t<float, py::array::c_style | py::array::forcecast>::ensure(o);
+    if (!a || a.ndim() != 1) throw CozoError("", "only 1-d float arrays convert to vectors");
+    return DataValue::from_vec(std::vector<float>(a.data(), a.data() + a.size()));
+  }
+  if (py::isinstance<py::list>(o) || py::isinstance<py::tuple>(o)) {
+    std::vector<DataValue> l;
+    for (auto x : o) l.push_back(to_dv(x));
+    return DataValue::from_list(std::move(l));
+  }
+  // numpy scalars
+  if (py::hasattr(o, "item")) return to_dv(o.attr("item")());
+  throw CozoError("", "unsupported python value");
+}
+
+static py::object from_dv(const DataValue& d) {
+  switch (d.kind) {
+    case DataValue::Null: return py::none();
+    case DataValue::Bool: return py::bool_(d.b);
+    case DataValue::Num: return d.is_float ? py::object(py::float_(d.f)) : py::object(py::int_(d.i));
+    case DataValue::Str: return py::str(d.s);
+    case DataValue::Bytes: return py::bytes(d.s);
+    case DataValue::List: {
+      py::list l;
+      for (auto& x : d.list) l.append(from_dv(x));
+      return l;
+    }
+    case DataValue::Vec: {
+      py::array_t<float> a(d.v->size());
+      std::copy(d.v->begin(), d.v->end(), a.mutable_data());
+      return a;
+    }
+    default: return py::none();
+  }
+}
+
+static Tuple to_tuple(const py::handle& row) {
+  Tuple t;
+  for (auto x : row) t.push_back(to_dv(x));
+  return t;
+}
+static py::list from_tuple(const Tuple& t) {
+  py::list l;
+  for (auto& x : t) l.append(from_dv(x));
+  return l;
+}
+static std::vector<Tuple> to_rows(const py::handle& rows) {
+  std::vector<Tuple> r;
+  for (auto x : rows) r.push_back(to_tuple(x));
+  return r;
+}
+static py::list from_rows(const std::vector<Tuple>& rows) {
+  py::list l;
+  for (auto& t : rows) l.append(from_tuple(t));
+  return l;
+}
+
+struct PyDb {
+  FixedRuleRegistry reg;
+  py::list run_fixed_rule(const std::string& name, py::list inputs, py::dict options, size_t head_arity,
+                          std::vector<size_t> input_arities, std::shared_ptr<Poison> poison) {
+    std::vector<std::vector<Tuple>> ins;
+    for (auto r : inputs) ins.push_back(to_rows(r));
+    Options opts;
+    for (auto kv : options) opts[kv.first.cast<std::string>()] = to_dv(kv.second);
+    Poison p = poison ? *poison : Poison();
+    return from_rows(reg.run(name, ins, input_arities, std::move(opts), head_arity, p));
+  }
+  void register_fixed_rule(const std::string& name, size_t arity, py::function fn) {
+    auto rule = std::make_shared<SimpleFixedRule>(
+        arity, [fn](const std::vector<std::vector<Tuple>>& ins, const Options& opts) -> std::vector<Tuple> {
+          py::list pins;
+          for (auto& r : ins) pins.append(from_rows(r));
+          py::dict popts;
+          for (auto& kv : opts) popts[py::str(kv.first)] = from_dv(kv.second);
+          return to_rows(fn(pins, popts));
+        });
+    reg.register_fixed_rule(name, rule);
+  }
+  bool unregister_fixed_rule(const std::string& name) { return reg.unregister_fixed_rule(name); }
+};
+
+struct PyRelation {
+  RelationHandle rel;
+  PyRelation(const std::string& name, std::vector<std::string> keys, std::vector<std::string> non_keys) {
+    rel.name = name;
+    rel.keys = std::move(keys);
+    rel.non_keys = std::move(non_keys);
+  }
+  void put(py::handle row) { rel.put(to_tuple(row)); }
+  size_t size() const { return rel.rows.size(); }
+};
+
+struct PyHnswIndex {
+  StagedHnswIndex ix;
+  void stage(const PyRelation& base, py::handle idx_rows, py::dict mf) {
+    HnswIndexManifest m;
+    m.vec_dim = mf["dim"].cast<size_t>();
+    m.m_neighbours = mf["m"].cast<size_t>();
+    m.ef_construction = mf["ef_construction"].cast<size_t>();
+    m.vec_fields = mf["fields"].cast<std::vector<size_t>>();
+    std::string dist = mf.contains("distance") ? mf["distance"].cast<std::string>() : "L2";
+    if (dist == "L2") m.distance = HnswDistance::L2;
+    else if (dist == "Cosine") m.distance = HnswDistance::Cosine;
+    else if (dist == "IP") m.distance = HnswDistance::InnerProduct;
+    else throw CozoError("", "Invalid distance: " + dist);  // sys.rs:584-590
+    std::string dt = mf.contains("dtype") ? mf["dtype"].cast<std::string>() : "F32";
+    if (dt == "F64" || dt == "Double") m.dtype_f64 = true;
+    else if (dt != "F32" && dt != "Float") throw CozoError("", "Invalid dtype: " + dt);  // sys.rs:567-573
+    m.derive();
+    ix.stage(base.rel, to_rows(idx_rows), m);
+  }
+  py::dict info() const {
+    py::dict d;
+    d["n_vectors"] = ix.keys.size();
+    d["edges_kept"] = ix.n_edges_kept;
+    d["dropped_same_key"] = ix.n_rows_dropped_same_key;
+    d["dropped_ignore_link"] = ix.n_rows_dropped_ignored;
+    return d;
+  }
+};
+
+struct PyHnswSearchRA {
+  HnswSearchRA ra;
+  std::shared_ptr<PyRelation> base;
+  std::shared_ptr<PyHnswIndex> index;
+  PyHnswSearchRA(std::shared_ptr<PyRelation> b, std::shared_ptr<PyHnswIndex> ix, size_t k, size_t ef, py::object radius,
+                 bool bind_field, bool bind_field_idx, bool bind_distance, bool bind_vector, py::object filter,
+                 size_t bind_idx)
+      : base(std::move(b)), index(std::move(ix)) {
+    ra.hnsw_search.base_handle = &base->rel;
+    ra.hnsw_search.index = &index->ix;
+    ra.hnsw_search.k = k;
+    ra.hnsw_search.ef = ef;
+    if (!radius.is_none()) ra.hnsw_search.radius = radius.cast<double>();
+    ra.hnsw_search.bind_field = bind_field;
+    ra.hnsw_search.bind_field_idx = bind_field_idx;
+    ra.hnsw_search.bind_distance = bind_distance;
+    ra.hnsw_search.bind_vector = bind_vector;
+    if (!filter.is_none()) {
+      py::function f = filter.cast<py::function>();
+      ra.hnsw_search.filter = [f](const Tuple& t) { return f(from_tuple(t)).cast<bool>(); };
+    }
+    ra.bind_idx = bind_idx;
+  }
+  py::list iter(py::handle parent) { return from_rows(ra.iter(to_rows(parent))); }
+  py::dict stats() const {
+    py::dict d;
+    d["n_queries"] = ra.last_stats.n_queries;
+    d["dist_evals"] = ra.last_stats.dist_evals;
+    d["nodes_expanded"] = ra.last_stats.nodes_expanded;
+    d["kernel_ms"] = ra.last_stats.kernel_ms;
+    return d;
+  }
+};
+
+PYBIND11_MODULE(_cozo_host, m) {
+  m.doc() = "test harness over the C++ host mirror of cozo's FixedRule / HnswSearchRA interfaces";
+  static py::exception<CozoError> exc(m, "CozoError");
+  py::register_exception_translator([](std::exception_ptr p) {
+    try {
+      if (p) std::rethrow_exception(p);
+    } catch (const CozoError& e) {
+      py::object ex = py::handle(exc.ptr())(e.what());
+      ex.attr("code") = py::str(e.code);
+      PyErr_SetObject(exc.ptr(), ex.ptr());
+    }
+  });
+  m.def("init", [](int dev) { gpu_check(cozo_gpu_init(dev)); });
+  py::class_<Poison, std::shared_ptr<Poison>>(m, "Poison").def(py::init<>()).def("kill", &Poison::kill);
+  py::class_<PyDb>(m, "Db")
+      .def(py::init<>())
+      .def("run_fixed_rule", &PyDb::run_fixed_rule, py::arg("name"), py::arg("inputs"), py::arg("options") = py::dict(),
+           py::arg("head_arity") = 0, py::arg("input_arities") = std::vector<size_t>(),
+           py::arg("poison") = std::shared_ptr<Poison>())
+      .def("register_fixed_rule", &PyDb::register_fixed_rule)
+      .def("unregister_fixed_rule", &PyDb::unregister_fixed_rule);
+  py::class_<PyRelation, std::shared_ptr<PyRelation>>(m, "Relation")
+      .def(py::init<const std::string&, std::vector<std::string>, std::vector<std::string>>())
+      .def("put", &PyRelation::put)
+      .def("__len__", &PyRelation::size);
+  py::class_<PyHnswIndex, std::shared_ptr<PyHnswIndex>>(m, "HnswIndex")
+      .def(py::init<>())
+      .def("stage", &PyHnswIndex::stage)
+      .def("info", &PyHnswIndex::info);
+  py::class_<PyHnswSearchRA>(m, "HnswSearchRA")
+      .def(py::init<std::shared_ptr<PyRelation>, std::shared_ptr<PyHnswIndex>, size_t, size_t, py::object, bool, bool,
+                    bool, bool, py::object, size_t>(),
+           py::arg("base"), py::arg("index"), py::arg("k"), py::arg("ef"), py::arg("radius") = py::none(),
+           py::arg("bind_field") = false, py::arg("bind_field_idx") = false, py::arg("bind_distance") = false,
+           py::arg("bind_vector") = false, py::arg("filter") = py::none(), py::arg("bind_idx") = 0)
+      .def("iter", &PyHnswSearchRA::iter)
+      .def("stats", &PyHnswSearchRA::stats);
+  m.def("cmp", [](py::handle a, py::handle b) { return cmp(to_dv(a), to_dv(b)); });
+}

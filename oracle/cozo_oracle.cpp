@@ -892,6 +892,50 @@ uint64_t orc_hnsw_build_dist_evals(void* hp) {
   return h->b ? h->b->dist_evals : 0;
 }
 
+// Raw rows of the index relation (runtime/relation.rs:1064-1126) in key order, for tests of
+// the host-side stager: self-loop rows (fr == to, value = degree), live and soft-deleted
+// edge rows.  The canary row (1, Null..) is added by the caller.  Returns the row count;
+// arrays may be NULL to size them.
+uint64_t orc_hnsw_relation_rows(void* hp, int64_t* layer, uint32_t* fr, uint32_t* to, double* dist,
+                                uint8_t* ignore_link) {
+  auto* h = (HnswHandle*)hp;
+  if (!h->b) return 0;
+  uint64_t c = 0;
+  for (auto& lr : h->b->rel) {  // most negative layer first
+    const LevelRel& L = lr.second;
+    for (auto& sd : L.self_degree) {
+      const uint32_t node = sd.first;
+      auto ei = L.edges.find(node);
+      bool self_done = false;
+      auto emit_self = [&] {
+        if (layer) {
+          layer[c] = lr.first;
+          fr[c] = node;
+          to[c] = node;
+          dist[c] = sd.second;
+          ignore_link[c] = 0;
+        }
+        ++c;
+        self_done = true;
+      };
+      if (ei != L.edges.end())
+        for (auto& kv : ei->second) {
+          if (!self_done && kv.first > node) emit_self();
+          if (layer) {
+            layer[c] = lr.first;
+            fr[c] = node;
+            to[c] = kv.first;
+            dist[c] = kv.second.dist;
+            ignore_link[c] = kv.second.ignore_link ? 1 : 0;
+          }
+          ++c;
+        }
+      if (!self_done) emit_self();
+    }
+  }
+  return c;
+}
+
 // -- read-only view from flat arrays (to search graphs built elsewhere) ------
 // level_nodes[L]: n rows on level L; node_ids[L] NULL for level 0 (identity).
 void* orc_hnsw_from_csr(uint32_t n, uint32_t dim, int metric, const float* vectors, int copy_vectors,

@@ -45,6 +45,8 @@ def lib():
         L.orc_hnsw_remove.argtypes = [vp, u32]
         L.orc_hnsw_build_dist_evals.restype = u64
         L.orc_hnsw_build_dist_evals.argtypes = [vp]
+        L.orc_hnsw_relation_rows.restype = u64
+        L.orc_hnsw_relation_rows.argtypes = [vp, vp, vp, vp, vp, vp]
         L.orc_hnsw_from_csr.restype = vp
         L.orc_hnsw_from_csr.argtypes = [u32, u32, C.c_int, vp, C.c_int, u32, vp, vp, vp, vp, u32]
         L.orc_hnsw_free.argtypes = [vp]
@@ -157,6 +159,18 @@ class OracleHnsw:
 
     def build_dist_evals(self) -> int:
         return lib().orc_hnsw_build_dist_evals(self._h)
+
+    def relation_rows(self):
+        """Raw index-relation rows in key order: (layer i64, fr u32, to u32, dist f64, ignore_link u8);
+        self-loop rows have fr == to and carry the degree in `dist`."""
+        n = lib().orc_hnsw_relation_rows(self._h, None, None, None, None, None)
+        layer = np.zeros(n, np.int64)
+        fr = np.zeros(n, np.uint32)
+        to = np.zeros(n, np.uint32)
+        dist = np.zeros(n, np.float64)
+        ign = np.zeros(n, np.uint8)
+        lib().orc_hnsw_relation_rows(self._h, _p(layer), _p(fr), _p(to), _p(dist), _p(ign))
+        return layer, fr, to, dist, ign
 
     def levels(self) -> HnswLevels:
         L = lib()

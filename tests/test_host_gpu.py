@@ -1,0 +1,248 @@
+"""GPU tests through the host layer: the FixedRule implementations and HnswSearchRA read
+like the reference's own tests (relations in, rows out) and are checked against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.hostmod import load
+from tests.util import uniform_vectors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def h(gpu):
+    m = load()
+    m.init(0)
+    return m
+
+
+def _edges(n, m, seed, weighted=True):
+    rng = np.random.default_rng(seed)
+    names = [f"n{i:04d}" for i in range(n)]
+    s = rng.integers(0, n, m)
+    d = rng.integers(0, n, m)
+    w = (rng.integers(1, 64, m) / 8.0)
+    # a stored relation is a set of tuples in key order
+    rows = sorted({(names[a], names[b], float(ww)) if weighted else (names[a], names[b]) for a, b, ww in zip(s, d, w)})
+    return names, [list(r) for r in rows]
+
+
+def _dense(rows, undirected=False):
+    """first-appearance ids (fixed_rule/mod.rs:164-179)"""
+    ids, src, dst, w = {}, [], [], []
+    for r in rows:
+        for k in r[:2]:
+            ids.setdefault(k, len(ids))
+        src.append(ids[r[0]])
+        dst.append(ids[r[1]])
+        w.append(r[2] if len(r) > 2 else 1.0)
+        if undirected:
+            src.append(ids[r[1]])
+            dst.append(ids[r[0]])
+            w.append(w[-1])
+    return ids, np.array(src, np.uint32), np.array(dst, np.uint32), np.array(w, np.float32)
+
+
+def test_pagerank_rule(h):
+    names, rows = _edges(300, 3000, 1, weighted=False)
+    db = h.Db()
+    for undirected in (False, True):
+        out = db.run_fixed_rule("PageRank", [rows], {"undirected": undirected, "iterations": 20, "epsilon": 0.0},
+                                head_arity=2)
+        ids, src, dst, _ = _dense(rows, undirected)
+        o = O.OracleGraph(len(ids), src, dst)
+        exp, it, _ = o.pagerank(0.85, 0.0, 20)
+        assert [r[0] for r in out] == sorted(ids)                      # BTreeMap order of RegularTempStore
+        got = np.array([r[1] for r in out])
+        ref = np.array([exp[ids[k]] for k in sorted(ids)], np.float64)
+        assert np.max(np.abs(got - ref) / ref) <= 1e-5
+    assert db.run_fixed_rule("PageRank", [[]], {}) == []                # empty relation => no rows (pagerank.rs:43-45)
+    with pytest.raises(h.CozoError) as e:
+        db.run_fixed_rule("PageRank", [[["a"]]], {})
+    assert e.value.code == "algo::not_an_edge"
+
+
+def test_pagerank_rule_can_be_killed(h):
+    _, rows = _edges(100, 500, 2, weighted=False)
+    p = h.Poison()
+    p.kill()
+    with pytest.raises(h.CozoError) as e:
+        h.Db().run_fixed_rule("PageRank", [rows], {}, poison=p)
+    assert e.value.code == "eval::killed"
+
+
+def test_dijkstra_rule(h):
+    names, rows = _edges(200, 1400, 3)
+    db = h.Db()
+    starts = [[names[0]], [names[5]], ["not-a-node"]]
+    goals = [[names[7]], [names[9]], [names[150]]]
+    out = db.run_fixed_rule("ShortestPathDijkstra", [rows, starts, goals], {}, head_arity=4)
+    ids, src, dst, w = _dense(rows)
+    o = O.OracleGraph(len(ids), src, dst, w)
+    wmap = {}
+    for a, b, ww in rows:
+        wmap[(a, b)] = min(wmap.get((a, b), 1e30), ww)
+    assert len(out) == 2 * 3
+    for start, goal, cost, path in out:
+        od, _ = o.sssp([ids[start]])
+        exp = float(od[0, ids[goal]])
+        if np.isinf(exp):
+            assert cost == float("inf") and path == []                 # shortest_path_dijkstra.rs:322-323
+            continue
+        assert cost == exp
+        assert path[0] == start and path[-1] == goal
+        assert abs(sum(wmap[(a, b)] for a, b in zip(path, path[1:])) - cost) < 1e-9
+    # no termination relation => every node is a goal (Goal for (), :233-235)
+    out = db.run_fixed_rule("ShortestPathDijkstra", [rows, [[names[0]]]], {})
+    assert len(out) == len(ids)
+    with pytest.raises(h.CozoError) as e:
+        db.run_fixed_rule("ShortestPathDijkstra", [[["a", "b", -1.0]], [["a"]]], {})
+    assert e.value.code == "algo::invalid_edge_weight"                 # mod.rs:273-286
+
+
+def test_dijkstra_keep_ties(h):
+    rows = [["a", "b", 1.0], ["a", "c", 1.0], ["b", "d", 1.0], ["c", "d", 1.0], ["a", "d", 5.0], ["d", "e", 1.0]]
+    db = h.Db()
+    out = db.run_fixed_rule("ShortestPathDijkstra", [rows, [["a"]], [["e"]]], {"keep_ties": True})
+    assert sorted(r[3] for r in out) == [["a", "b", "d", "e"], ["a", "c", "d", "e"]]
+    assert all(r[2] == 3.0 for r in out)
+    out = db.run_fixed_rule("ShortestPathDijkstra", [rows, [["a"]], [["e"]]], {})
+    assert len(out) == 1 and out[0][2] == 3.0
+    # undirected mirrors every edge (mod.rs:313-317)
+    out = db.run_fixed_rule("ShortestPathDijkstra", [rows, [["e"]], [["a"]]], {"undirected": True})
+    assert out[0][2] == 3.0
+
+
+def test_centrality_rules(h):
+    names, rows = _edges(150, 900, 4)
+    db = h.Db()
+    ids, src, dst, w = _dense(rows)
+    o = O.OracleGraph(len(ids), src, dst, w)
+    keys = sorted(ids)
+    out = db.run_fixed_rule("ClosenessCentrality", [rows], {}, head_arity=2)
+    ref = o.closeness(n_threads=8)
+    got = np.array([r[1] for r in out])
+    exp = np.array([ref[ids[k]] for k in keys], np.float64)
+    assert [r[0] for r in out] == keys
+    fin = np.isfinite(exp)
+    assert np.allclose(got[fin], exp[fin], rtol=1e-5) and np.array_equal(np.isfinite(got), fin)
+    out = db.run_fixed_rule("BetweennessCentrality", [rows], {}, head_arity=2)
+    ref = o.betweenness(n_threads=8)
+    got = np.array([r[1] for r in out])
+    exp = np.array([ref[ids[k]] for k in keys], np.float64)
+    assert np.allclose(got, exp, rtol=1e-4, atol=1e-4)
+
+
+def _index_relation(ix, key_of, field_idx, K=1):
+    """raw rows of `rel:idx` (runtime/relation.rs:1064-1126) from the oracle's faithful builder"""
+    layer, fr, to, dist, ign = ix.relation_rows()
+    rows = []
+    for l, f, t, d, g in zip(layer, fr, to, dist, ign):
+        self_loop = f == t
+        rows.append([int(l)] + key_of(int(f)) + [field_idx, -1] + key_of(int(t)) + [field_idx, -1] +
+                    [float(d), b"hash" if self_loop else None, bool(g)])
+    rows.append([1] + [None] * (2 * K + 4) + [int(layer.min()), b"canary", False])      # canary (hnsw.rs:642-669)
+    return rows
+
+
+def test_hnsw_search_ra(h):
+    """?[dist, k, v] := *q[qid, qv], ~a:vec{k, v | query: qv, k: 5, ef: 40, bind_distance: dist}"""
+    n, dim, m = 1500, 32, 8
+    X = uniform_vectors(n, dim, 31)
+    ix = O.OracleHnsw.new(n, dim, m=m, ef_construction=50)
+    ix.insert_all(X)
+    base = h.Relation("a", ["k"], ["v", "tag"])
+    names = [f"key{i:05d}" for i in range(n)]                          # string keys: key order == id order
+    for i in range(n):
+        base.put([names[i], X[i], i % 7])
+    idx_rows = _index_relation(ix, lambda i: [names[i]], 1)
+    index = h.HnswIndex()
+    index.stage(base, idx_rows, {"dim": dim, "m": m, "ef_construction": 50, "fields": [1]})
+    info = index.info()
+    assert info["n_vectors"] == n and info["dropped_ignore_link"] > 0 and info["dropped_same_key"] >= n
+    Q = uniform_vectors(60, dim, 32)
+    parent = [[qi, Q[qi]] for qi in range(60)]
+    ra = h.HnswSearchRA(base, index, k=5, ef=40, bind_distance=True, bind_idx=1)
+    out = ra.iter(parent)
+    oi, od, oc, _ = ix.search(Q, 5, 40)
+    assert len(out) == 60 * 5
+    for qi in range(60):
+        rows = [r for r in out if r[0] == qi]
+        assert [r[2] for r in rows] == [names[j] for j in oi[qi]]      # parent ++ base row ++ distance, nearest first
+        assert np.allclose([r[5] for r in rows], od[qi], rtol=1e-5)
+        assert all(r[4] == int(r[2][3:]) % 7 for r in rows)
+    assert ra.stats()["n_queries"] == 60
+    # all bindings, in the order of HnswSearch::all_bindings (program.rs:1016-1025)
+    ra = h.HnswSearchRA(base, index, k=2, ef=40, bind_field=True, bind_field_idx=True, bind_distance=True,
+                        bind_vector=True, bind_idx=1)
+    row = ra.iter(parent[:1])[0]
+    assert row[5] == "v" and row[6] is None and isinstance(row[7], float) and np.array_equal(row[8], row[3])
+    # radius + filter: the filter sees the assembled row; k is applied after it (hnsw.rs:943-947,997-1006)
+    ra = h.HnswSearchRA(base, index, k=3, ef=40, bind_distance=True, bind_idx=1, filter=lambda r: r[4] != 0)
+    out = ra.iter(parent)
+    oi40, od40, _, _ = ix.search(Q, 40, 40)
+    for qi in range(60):
+        exp = [names[j] for j in oi40[qi] if j % 7 != 0][:3]
+        assert [r[2] for r in out if r[0] == qi] == exp
+    r0 = float(np.median(od[:, 2]))
+    ra = h.HnswSearchRA(base, index, k=5, ef=40, radius=r0, bind_distance=True, bind_idx=1)
+    out = ra.iter(parent)
+    assert all(r[5] <= r0 for r in out) and len(out) == int((od <= r0).sum())
+    # error behaviour of the operator
+    with pytest.raises(h.CozoError) as e:
+        h.HnswSearchRA(base, index, k=5, ef=40, bind_idx=1).iter([[0, "not a vector"]])
+    assert "Expected vector" in str(e.value)                           # ra.rs:1106-1109
+    with pytest.raises(h.CozoError) as e:
+        h.HnswSearchRA(base, index, k=5, ef=40, bind_idx=0).iter([[np.zeros(7, np.float32)]])
+    assert "dimension mismatch" in str(e.value)                        # hnsw.rs:876-878
+    with pytest.raises(h.CozoError):
+        h.HnswSearchRA(base, index, k=0, ef=40, bind_idx=1).iter(parent)
+    # f64 query vectors are cast to the index dtype (hnsw.rs:879-884)
+    out64 = h.HnswSearchRA(base, index, k=5, ef=40, bind_idx=1).iter([[0, Q[0].astype(np.float64)]])
+    assert [r[2] for r in out64] == [names[j] for j in oi[0]]
+
+
+def test_hnsw_multi_vector_rows_and_empty_index(h):
+    """a list-of-vectors column: sibling vectors of one row never link to each other (hnsw.rs:609)"""
+    dim, m = 16, 4
+    X = uniform_vectors(200, dim, 41)
+    base = h.Relation("docs", ["id"], ["chunks"])
+    for r in range(100):
+        base.put([r, [X[2 * r], X[2 * r + 1]]])
+    # compound keys (row, field=1, sub) in key order: id = 2*row + sub
+    ix = O.OracleHnsw.new(200, dim, m=m, ef_construction=30)
+    ix.insert_all(X)
+    layer, fr, to, dist, ign = ix.relation_rows()
+    rows = []
+    for l, f, t, d, g in zip(layer, fr, to, dist, ign):
+        rows.append([int(l), int(f) // 2, 1, int(f) % 2, int(t) // 2, 1, int(t) % 2, float(d), None, bool(g)])
+    rows.append([1, None, None, None, None, None, None, int(layer.min()), b"c", False])
+    index = h.HnswIndex()
+    index.stage(base, rows, {"dim": dim, "m": m, "ef_construction": 30, "fields": [1]})
+    # oracle view with the same-row edges removed
+    lv = ix.levels()
+    for L in range(lv.n_levels):
+        nid = np.arange(200) if L == 0 else lv.node_ids[L]
+        rp, ci, new_rp, new_ci = lv.row_ptr[L], lv.col_idx[L], [0], []
+        for r_i, node in enumerate(nid):
+            new_ci += [c for c in ci[rp[r_i]:rp[r_i + 1]] if c // 2 != node // 2]
+            new_rp.append(len(new_ci))
+        lv.row_ptr[L], lv.col_idx[L] = np.array(new_rp, np.uint64), np.array(new_ci, np.uint32)
+    view = O.OracleHnsw.from_levels(X, lv)
+    Q = uniform_vectors(30, dim, 42)
+    ra = h.HnswSearchRA(base, index, k=4, ef=30, bind_field_idx=True, bind_distance=True, bind_idx=0)
+    out = ra.iter([[q] for q in Q])
+    oi, od, oc, _ = view.search(Q, 4, 30)
+    k = 0
+    for qi in range(30):
+        for j in range(oc[qi]):
+            r = out[k]
+            k += 1
+            assert (r[1], r[3]) == (int(oi[qi, j]) // 2, int(oi[qi, j]) % 2)
+    assert k == len(out)
+    # an index holding only the canary row returns nothing (hnsw.rs:903-909)
+    empty = h.HnswIndex()
+    empty.stage(base, [[1, None, None, None, None, None, None, 0, b"c", False]],
+                {"dim": dim, "m": m, "ef_construction": 30, "fields": [1]})
+    assert h.HnswSearchRA(base, empty, k=4, ef=30, bind_idx=0).iter([[Q[0]]]) == []
