@@ -82,7 +82,7 @@ struct BatchParams {
 
 // K1 ------------------------------------------------------------------------
 template <int NV, int METRIC>
-__global__ void __launch_bounds__(256, 2) build_search_kernel(HnswDev g, BuildDev b, BatchParams p) {
+__global__ void __launch_bounds__(128, 4) build_search_kernel(HnswDev g, BuildDev b, BatchParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -521,7 +521,7 @@ extern "C" int cozo_gpu_hnsw_build(cozo_gpu_hnsw_t** out, const CozoGpuHnswBuild
   const uint32_t ef_c = d->ef_construction;
   uint32_t max_batch = d->max_batch ? d->max_batch : 8192;
   uint32_t wpc = (uint32_t)get_option("hnsw.warps_per_cta", 4);
-  wpc = std::min(8u, std::max(1u, wpc));
+  wpc = std::min(4u, std::max(1u, wpc));
   uint32_t ns = (uint32_t)get_option("hnsw.stages", 4);
   ns = std::min(32u, std::max(1u, ns));
   SmemLayout lay = make_layout(ef_c, ns, g.ld);

@@ -250,6 +250,12 @@ __device__ __forceinline__ void search_level(const HnswDev& g, WarpCtx& w, const
     if (lane == 0) w.fi[ci] = cand | EXPANDED;
     w.cursor = ci + 1;
     w.nodes_expanded++;
+    if (level == 0 && ci + 1 + lane < w.len && lane < 2) {
+      // the next pop is most likely one of the following entries: pull their adjacency rows into L2
+      uint32_t nxt = w.fi[ci + 1 + lane];
+      if (!(nxt & EXPANDED))
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(g.adj0 + (size_t)nxt * g.s0));
+    }
     // hnsw_get_neighbours (hnsw.rs:588-629): one padded row
     const uint32_t* row;
     if (level == 0) {
@@ -270,27 +276,28 @@ __device__ __forceinline__ void search_level(const HnswDev& g, WarpCtx& w, const
       __syncwarp();
       w.dist_evals += cnt;
       if (BULK) {
-        uint32_t issued = 0;
+        // ring indices advance by compare-and-wrap (a runtime `% ns` costs ~20 instructions)
+        uint32_t issued = 0, si = w.head, sc = w.head;
         for (uint32_t c = 0; c < cnt; ++c) {
           if (lane == 0) {
             fence_proxy_async_smem();
             while (issued < cnt && issued - c < w.ns) {
-              uint32_t s = (w.head + issued) % w.ns;
-              mbar_expect_tx(&w.bars[s], row_bytes);
-              bulk_g2s(w.ring + (size_t)s * g.ld, g.vec + (size_t)w.pend[issued] * g.ld, row_bytes, &w.bars[s]);
+              mbar_expect_tx(&w.bars[si], row_bytes);
+              bulk_g2s(w.ring + (size_t)si * g.ld, g.vec + (size_t)w.pend[issued] * g.ld, row_bytes, &w.bars[si]);
               ++issued;
+              if (++si == w.ns) si = 0;
             }
           }
-          uint32_t s = (w.head + c) % w.ns;
-          mbar_wait(&w.bars[s], (w.phase >> s) & 1u);
-          w.phase ^= (1u << s);
-          float d = dist_smem<NV, METRIC>(q, reinterpret_cast<const float4*>(w.ring + (size_t)s * g.ld), lane, nvec4,
+          mbar_wait(&w.bars[sc], (w.phase >> sc) & 1u);
+          w.phase ^= (1u << sc);
+          float d = dist_smem<NV, METRIC>(q, reinterpret_cast<const float4*>(w.ring + (size_t)sc * g.ld), lane, nvec4,
                                           qnorm);
+          if (++sc == w.ns) sc = 0;
           uint32_t nid = w.pend[c];
           __syncwarp();
           if (w.len < ef || d < w.fd[w.len - 1]) sorted_insert(w, ef, d, nid, lane);  // hnsw.rs:575-581
         }
-        w.head = (w.head + cnt) % w.ns;
+        w.head = sc;
       } else {
         for (uint32_t c = 0; c < cnt; c += 2) {
           uint32_t id0 = w.pend[c];

@@ -170,3 +170,28 @@ def test_betweenness_parity(gpu):
     ob = o.betweenness(n_threads=8)
     assert np.allclose(gb, ob, rtol=1e-4, atol=1e-4)
     assert ob.max() > 10
+
+
+# ---- the reference's air-routes fixture as input ----------------------------------------
+def test_air_routes_all_rules(gpu):
+    from tests.test_air_routes_cpu import load_routes
+    n, src, dst, dist, id_of, _ = load_routes()
+    g = gpu.Graph(n, src, dst, dist)
+    o = O.OracleGraph(n, src, dst, dist)
+    starts = np.array([id_of[c] for c in ("JFK", "LHR", "SYD", "AUS", "KUL")], np.uint32)
+    gd, gp, _ = g.sssp(starts)
+    od, _ = o.sssp(starts, n_threads=8)
+    assert np.array_equal(gd, od)
+    _check_tree(src, dst, dist, starts, gd, gp, n)
+    gc, _ = g.closeness()
+    oc = o.closeness(n_threads=16)
+    fin = np.isfinite(oc)
+    assert np.array_equal(np.isfinite(gc), fin) and np.allclose(gc[fin], oc[fin], rtol=1e-5)
+    gb, _ = g.betweenness()
+    ob = o.betweenness(n_threads=16)
+    assert np.allclose(gb, ob, rtol=2e-4, atol=1e-3)
+    g2 = gpu.Graph(n, src, dst)
+    o2 = O.OracleGraph(n, src, dst)
+    gs, git, _, _ = g2.pagerank(0.85, 1e-4, 10)
+    os_, oit, _ = o2.pagerank(0.85, 1e-4, 10)
+    assert git == oit and np.max(np.abs(gs - os_) / os_) <= 1e-5

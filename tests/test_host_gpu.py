@@ -179,7 +179,7 @@ def test_hnsw_search_ra(h):
     row = ra.iter(parent[:1])[0]
     assert row[5] == "v" and row[6] is None and isinstance(row[7], float) and np.array_equal(row[8], row[3])
     # radius + filter: the filter sees the assembled row; k is applied after it (hnsw.rs:943-947,997-1006)
-    ra = h.HnswSearchRA(base, index, k=3, ef=40, bind_distance=True, bind_idx=1, filter=lambda r: r[4] != 0)
+    ra = h.HnswSearchRA(base, index, k=3, ef=40, bind_distance=True, bind_idx=1, filter=lambda r: r[2] != 0)   # r = base row ++ bindings
     out = ra.iter(parent)
     oi40, od40, _, _ = ix.search(Q, 40, 40)
     for qi in range(60):

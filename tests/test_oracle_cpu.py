@@ -271,3 +271,23 @@ def test_closeness_and_betweenness_vs_networkx():
 def test_rmat_generator_shape():
     n, s, d = rmat_edges(10, 16, 0x5EED0004)
     assert n == 1024 and s.size == 16384 and s.max() < n and d.max() < n
+
+
+def test_frozen_oracle_outputs():
+    """tests/golden/oracle_small.npz (made by tests/golden/make_oracle_golden.py): the oracle must keep
+    producing what it produced when the fixtures were frozen."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_small.npz"))
+    ix = O.OracleHnsw.new(600, 24, m=6, ef_construction=40, level_seed=SEED_LEVEL)
+    ix.insert_all(z["X"])
+    lv = ix.levels()
+    assert lv.entry == int(z["entry"]) and lv.n_levels == int(z["n_levels"])
+    assert np.array_equal(np.diff(lv.row_ptr[0]), z["deg0"]) and np.array_equal(lv.col_idx[0], z["col0"])
+    ids, dist, cnt, st = ix.search(z["Q"], 8, 32)
+    assert np.array_equal(ids, z["ids"]) and np.array_equal(dist, z["dist"]) and np.array_equal(st, z["stats"])
+    g = O.OracleGraph(200, z["src"], z["dst"], z["w"])
+    pr, it, _ = O.OracleGraph(200, z["src"], z["dst"]).pagerank(0.85, 1e-4, 10)
+    assert it == int(z["pr_iters"]) and np.array_equal(pr, z["pr"])
+    sd, _ = g.sssp(np.arange(0, 200, 25, dtype=np.uint32))
+    assert np.array_equal(sd, z["sssp"])
+    assert np.array_equal(g.closeness(), z["closeness"]) and np.array_equal(g.betweenness(), z["betweenness"])

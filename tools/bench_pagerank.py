@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""PageRank on synthetic RMAT (BASELINE configs[3]: scale 24, edge factor 16) — secondary bench.
+Prints one JSON line: time/iter, achieved GB/s against the 8E+20N bytes/iter model, oracle timing."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rmat_torch(scale, ef, seed, a=0.57, b=0.19, c=0.19):
+    import torch
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    n, m = 1 << scale, (1 << scale) * ef
+    src = torch.zeros(m, dtype=torch.int64, device="cuda")
+    dst = torch.zeros(m, dtype=torch.int64, device="cuda")
+    for bit in range(scale):
+        r = torch.rand(m, device="cuda", generator=gen)
+        sbit = r >= a + b
+        dbit = ((r >= a) & (r < a + b)) | (r >= a + b + c)
+        src |= sbit.long() << bit
+        dst |= dbit.long() << bit
+    perm = torch.randperm(n, device="cuda", generator=gen)
+    return n, perm[src].to(torch.int32).cpu().numpy().view(np.uint32), perm[dst].to(torch.int32).cpu().numpy().view(np.uint32)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=int, default=24)
+    ap.add_argument("--edge-factor", type=int, default=16)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    from cozo_b200 import capi
+    capi.init(0)
+    t0 = time.perf_counter()
+    n, src, dst = rmat_torch(a.scale, a.edge_factor, 0x5EED0004)
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    g = capi.Graph(n, src, dst)
+    stage_s = time.perf_counter() - t0
+    m = src.size
+    best = None
+    for _ in range(a.reps):
+        scores, it, err, ms = g.pagerank(0.85, 0.0, a.iters)     # epsilon=0: exactly `iters` iterations
+        best = ms if best is None else min(best, ms)
+    s_def, it_def, err_def, ms_def = g.pagerank(0.85, 1e-4, a.iters)   # reference defaults
+    bytes_iter = 8 * m + 20 * n
+    out = {"workload": f"RMAT scale {a.scale} ef {a.edge_factor}: n={n} m={m}", "iters": a.iters,
+           "ms_total_best": best, "ms_per_iter": best / a.iters, "bytes_per_iter_model": bytes_iter,
+           "achieved_GBs": bytes_iter / (best / a.iters / 1e3) / 1e9,
+           "frac_of_measured_hbm": bytes_iter / (best / a.iters / 1e3) / 1e9 / 6574.5,
+           "defaults_run": {"iters": it_def, "err": err_def, "ms": ms_def}, "gen_s": gen_s, "stage_s": stage_s}
+    if not a.no_cpu:
+        from oracle import oracle as O
+        cores = os.cpu_count()
+        t0 = time.perf_counter()
+        o = O.OracleGraph(n, src, dst)
+        build_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        os_, oit, oerr = o.pagerank(0.85, 0.0, a.iters, n_threads=cores)
+        cpu_s = time.perf_counter() - t0
+        rel = np.abs(scores - os_) / os_
+        out["cpu_oracle"] = {"cores": cores, "s_total": cpu_s, "ms_per_iter": 1e3 * cpu_s / a.iters,
+                             "csr_build_s": build_s, "max_rel_err_gpu_vs_oracle": float(rel.max()),
+                             "p999_rel_err": float(np.quantile(rel, 0.999))}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
