@@ -22,11 +22,15 @@ struct cozo_gpu_graph {
   float* out_w = nullptr;
   uint32_t* hubs = nullptr;  // rows with in-degree > HUB_T
   uint32_t n_hubs = 0;
+  uint32_t* blk_start = nullptr;  // [n_blk+1] row blocks of the pull kernel (no hub row inside a block)
+  uint32_t n_blk = 0;
 };
 
 namespace cozo {
 
-constexpr uint32_t HUB_T = 2048;
+constexpr uint32_t HUB_T = 1024;    // rows longer than this get a CTA of their own (tree sum)
+constexpr uint32_t BLK_CAP = 2048;  // in-edges staged in shared memory per row block
+constexpr uint32_t BLK_ROWS = 1024; // rows per block
 
 __global__ void edge_check_kernel(const uint32_t* src, const uint32_t* dst, const float* w, uint64_t m, uint32_t n,
                                   int* bad) {
@@ -99,37 +103,71 @@ __device__ __forceinline__ void block_add_err(double e, double* out) {
   }
 }
 
-__global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict__ in_ptr,
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float ldg_f32_hint(const float* a, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t* a, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+
+// CSR-stream pull: a CTA owns a block of consecutive rows with <= BLK_CAP in-edges in total.
+// Phase 1 streams the block's in_idx slice (coalesced, evict-first) and gathers contrib[v]
+// (4 independent gathers per thread in flight; contrib is 4N bytes and is asked to stay in L2)
+// into shared memory; phase 2 sums every row's slice IN IN-NEIGHBOUR ORDER with one thread,
+// which is the order `.sum::<f32>()` uses in graph::page_rank, so these rows match a
+// sequential CPU run bit for bit.
+__global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict__ blk_start, uint32_t n_blk,
+                                                      const uint32_t* __restrict__ in_ptr,
                                                       const uint32_t* __restrict__ in_idx,
-                                                      const uint32_t* __restrict__ out_ptr, uint32_t n, float base,
-                                                      float damping, const float* __restrict__ contrib_old,
+                                                      const uint32_t* __restrict__ out_ptr, float base, float damping,
+                                                      const float* __restrict__ contrib_old,
                                                       float* __restrict__ contrib_new, float* __restrict__ scores,
                                                       double* err) {
-  const uint32_t sub = threadIdx.x & 7;
-  const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const uint32_t ngroups = (gridDim.x * blockDim.x) >> 3;
+  __shared__ float vals[BLK_CAP];
+  const uint64_t keep = l2_policy_evict_last();
+  const uint64_t stream = l2_policy_evict_first();
   double e = 0.0;
-  for (uint32_t u0 = group; u0 < ((n + 3) & ~3u); u0 += ngroups) {  // keep all 32 lanes in the shuffles
-    const bool live = u0 < n;
-    uint32_t b = 0, en = 0;
-    if (live) {
-      b = in_ptr[u0];
-      en = in_ptr[u0 + 1];
+  for (uint32_t blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+    const uint32_t r0 = blk_start[2 * blk], r1 = blk_start[2 * blk + 1];  // [r0,r1) pairs
+    const uint32_t e0 = in_ptr[r0], e1 = in_ptr[r1];
+    uint32_t k = e0 + threadIdx.x;
+    for (; k + 768 < e1; k += 1024) {
+      uint32_t i0 = ldg_u32_hint(in_idx + k, stream), i1 = ldg_u32_hint(in_idx + k + 256, stream);
+      uint32_t i2 = ldg_u32_hint(in_idx + k + 512, stream), i3 = ldg_u32_hint(in_idx + k + 768, stream);
+      float v0 = ldg_f32_hint(contrib_old + i0, keep), v1 = ldg_f32_hint(contrib_old + i1, keep);
+      float v2 = ldg_f32_hint(contrib_old + i2, keep), v3 = ldg_f32_hint(contrib_old + i3, keep);
+      vals[k - e0] = v0;
+      vals[k - e0 + 256] = v1;
+      vals[k - e0 + 512] = v2;
+      vals[k - e0 + 768] = v3;
     }
-    const bool hub = en - b > HUB_T;
-    float s = 0.f;
-    if (!hub)
-      for (uint32_t k = b + sub; k < en; k += 8) s += contrib_old[in_idx[k]];
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (live && !hub && sub == 0) {
-      float nw = base + damping * s;
-      e += (double)fabsf(nw - scores[u0]);
-      scores[u0] = nw;
-      uint32_t od = out_ptr[u0 + 1] - out_ptr[u0];
-      contrib_new[u0] = od ? nw / (float)od : 0.f;
+    for (; k < e1; k += 256) vals[k - e0] = ldg_f32_hint(contrib_old + ldg_u32_hint(in_idx + k, stream), keep);
+    __syncthreads();
+    for (uint32_t r = r0 + threadIdx.x; r < r1; r += 256) {
+      const uint32_t b = in_ptr[r] - e0, en = in_ptr[r + 1] - e0;
+      float s = 0.f;
+      for (uint32_t j = b; j < en; ++j) s += vals[j];
+      const float nw = base + damping * s;
+      e += (double)fabsf(nw - scores[r]);
+      scores[r] = nw;
+      const uint32_t od = out_ptr[r + 1] - out_ptr[r];
+      contrib_new[r] = od ? nw / (float)od : 0.f;
     }
+    __syncthreads();
   }
   block_add_err(e, err);
 }
@@ -386,7 +424,7 @@ using namespace cozo;
 
 extern "C" void cozo_gpu_graph_free(cozo_gpu_graph_t* g) {
   if (!g) return;
-  void* ptrs[] = {g->out_ptr, g->out_idx, g->in_ptr, g->in_idx, g->out_w, g->hubs};
+  void* ptrs[] = {g->out_ptr, g->out_idx, g->in_ptr, g->in_idx, g->out_w, g->hubs, g->blk_start};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete g;
@@ -491,12 +529,32 @@ extern "C" int cozo_gpu_graph_stage(cozo_gpu_graph_t** out, uint32_t n, uint64_t
     G_CUDA(cudaDeviceSynchronize());
   }
   if (n) {
-    DevBuf cnt;
-    G_CUDA(cudaMalloc(&g->hubs, (size_t)n * 4));
-    G_CUDA(cudaMalloc(&cnt.p, 4));
-    G_CUDA(cudaMemset(cnt.p, 0, 4));
-    find_hubs_kernel<<<(n + 255) / 256, 256>>>(g->in_ptr, n, g->hubs, cnt.as<uint32_t>());
-    G_CUDA(cudaMemcpy(&g->n_hubs, cnt.p, 4, cudaMemcpyDeviceToHost));
+    // row blocks for the pull kernel: consecutive rows, <= BLK_CAP in-edges and <= BLK_ROWS rows,
+    // hub rows (in-degree > HUB_T) excluded and listed separately
+    std::vector<uint32_t> hin(np1);
+    G_CUDA(cudaMemcpy(hin.data(), g->in_ptr, np1 * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> blocks, hubs;
+    uint32_t r = 0;
+    while (r < n) {
+      if (hin[r + 1] - hin[r] > HUB_T) {
+        hubs.push_back(r++);
+        continue;
+      }
+      const uint32_t r0 = r;
+      while (r < n && r - r0 < BLK_ROWS && hin[r + 1] - hin[r] <= HUB_T && hin[r + 1] - hin[r0] <= BLK_CAP) ++r;
+      blocks.push_back(r0);
+      blocks.push_back(r);
+    }
+    // blocks are [r0,r1) pairs; store starts and ends interleaved as consecutive pairs
+    g->n_blk = (uint32_t)(blocks.size() / 2);
+    g->n_hubs = (uint32_t)hubs.size();
+    // pack as start array with explicit end: pr_iter_kernel reads blk_start[blk], blk_start[blk+1];
+    // gaps (hub rows) make blocks non-contiguous, so keep pairs in a 2*n_blk array
+    G_CUDA(cudaMalloc(&g->blk_start, std::max<size_t>(blocks.size(), 2) * 4));
+    if (!blocks.empty())
+      G_CUDA(cudaMemcpy(g->blk_start, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice));
+    G_CUDA(cudaMalloc(&g->hubs, std::max<size_t>(hubs.size(), 1) * 4));
+    if (!hubs.empty()) G_CUDA(cudaMemcpy(g->hubs, hubs.data(), hubs.size() * 4, cudaMemcpyHostToDevice));
   }
 #undef G_CUDA
   *out = g;
@@ -544,7 +602,7 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   float* cnew = c1.as<float>();
   uint32_t iter = 0;
   double herr = 0;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)di.sm_count * 8 * 4);
+  const uint32_t grid = std::max(1u, std::min<uint32_t>(g->n_blk, (uint32_t)di.sm_count * 8 * 4));
   int ret = 0;
   for (;;) {
     if (poisoned(poison)) {
@@ -552,8 +610,9 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
       break;
     }
     cudaMemsetAsync(err.p, 0, 8);
-    pr_iter_kernel<<<grid, 256>>>(g->in_ptr, g->in_idx, g->out_ptr, n, base, damping, cold, cnew, scores.as<float>(),
-                                  err.as<double>());
+    if (g->n_blk)
+      pr_iter_kernel<<<grid, 256>>>(g->blk_start, g->n_blk, g->in_ptr, g->in_idx, g->out_ptr, base, damping, cold,
+                                    cnew, scores.as<float>(), err.as<double>());
     if (g->n_hubs)
       pr_hub_kernel<<<g->n_hubs, 256>>>(g->hubs, g->in_ptr, g->in_idx, g->out_ptr, base, damping, cold, cnew,
                                         scores.as<float>(), err.as<double>());
