@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # workload (defaults = BASELINE configs[1]); overridable for quick runs
-    ap.add_argument("--n", type=int, default=int(os.environ.get("COZO_BENCH_N", 1_000_000)))
+    ap.add_argument("--rows", dest="n", type=int, default=int(os.environ.get("COZO_BENCH_N", 1_000_000)))
     ap.add_argument("--dim", type=int, default=int(os.environ.get("COZO_BENCH_DIM", 768)))
     ap.add_argument("--batch", type=int, default=int(os.environ.get("COZO_BENCH_BATCH", 4096)))
     ap.add_argument("--ef", type=int, default=200)

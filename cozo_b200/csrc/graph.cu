@@ -22,8 +22,11 @@ struct cozo_gpu_graph {
   float* out_w = nullptr;
   uint32_t* hubs = nullptr;  // rows with in-degree > HUB_T
   uint32_t n_hubs = 0;
-  uint32_t* blk_start = nullptr;  // [n_blk+1] row blocks of the pull kernel (no hub row inside a block)
+  uint32_t* blk_start = nullptr;  // [2*n_blk] row blocks [r0,r1) of the pull kernel (no hub row inside a block)
   uint32_t n_blk = 0;
+  // hub rows are cut into chunks of <= HUB_CHUNK in-edges, one CTA per chunk
+  uint32_t *hub_chunk_ptr = nullptr, *chunk_beg = nullptr, *chunk_end = nullptr;
+  uint32_t n_chunks = 0;
 };
 
 namespace cozo {
@@ -31,6 +34,7 @@ namespace cozo {
 constexpr uint32_t HUB_T = 1024;    // rows longer than this get a CTA of their own (tree sum)
 constexpr uint32_t BLK_CAP = 2048;  // in-edges staged in shared memory per row block
 constexpr uint32_t BLK_ROWS = 1024; // rows per block
+constexpr uint32_t HUB_CHUNK = 4096; // in-edges of a hub row summed by one CTA
 
 __global__ void edge_check_kernel(const uint32_t* src, const uint32_t* dst, const float* w, uint64_t m, uint32_t n,
                                   int* bad) {
@@ -172,34 +176,58 @@ __global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict
   block_add_err(e, err);
 }
 
-__global__ void __launch_bounds__(256) pr_hub_kernel(const uint32_t* __restrict__ hubs,
-                                                     const uint32_t* __restrict__ in_ptr,
-                                                     const uint32_t* __restrict__ in_idx,
-                                                     const uint32_t* __restrict__ out_ptr, float base, float damping,
-                                                     const float* __restrict__ contrib_old,
-                                                     float* __restrict__ contrib_new, float* __restrict__ scores,
-                                                     double* err) {
-  __shared__ float sh[32];
-  const uint32_t u = hubs[blockIdx.x];
-  const uint32_t b = in_ptr[u], en = in_ptr[u + 1];
-  float s = 0.f;
-  for (uint32_t k = b + threadIdx.x; k < en; k += blockDim.x) s += contrib_old[in_idx[k]];
-  s = warp_sum(s);
+// Hub rows (in-degree > HUB_T): one CTA per chunk of <= HUB_CHUNK in-edges writes a partial sum
+// (fixed tree => deterministic), then one thread per hub row adds its partials in chunk order.
+__global__ void __launch_bounds__(256) pr_hub_partial_kernel(const uint32_t* __restrict__ chunk_beg,
+                                                             const uint32_t* __restrict__ chunk_end,
+                                                             const uint32_t* __restrict__ in_idx,
+                                                             const float* __restrict__ contrib_old,
+                                                             float* __restrict__ partial) {
+  __shared__ float sh[8];
+  const uint64_t keep = l2_policy_evict_last();
+  const uint64_t stream = l2_policy_evict_first();
+  const uint32_t b = chunk_beg[blockIdx.x], en = chunk_end[blockIdx.x];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  uint32_t k = b + threadIdx.x;
+  for (; k + 768 < en; k += 1024) {
+    uint32_t i0 = ldg_u32_hint(in_idx + k, stream), i1 = ldg_u32_hint(in_idx + k + 256, stream);
+    uint32_t i2 = ldg_u32_hint(in_idx + k + 512, stream), i3 = ldg_u32_hint(in_idx + k + 768, stream);
+    s0 += ldg_f32_hint(contrib_old + i0, keep);
+    s1 += ldg_f32_hint(contrib_old + i1, keep);
+    s2 += ldg_f32_hint(contrib_old + i2, keep);
+    s3 += ldg_f32_hint(contrib_old + i3, keep);
+  }
+  for (; k < en; k += 256) s0 += ldg_f32_hint(contrib_old + ldg_u32_hint(in_idx + k, stream), keep);
+  float s = warp_sum((s0 + s1) + (s2 + s3));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) sh[warp] = s;
   __syncthreads();
-  if (warp == 0) {
-    float v = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.f;
-    v = warp_sum(v);
-    if (lane == 0) {
-      float nw = base + damping * v;
-      double e = (double)fabsf(nw - scores[u]);
-      scores[u] = nw;
-      uint32_t od = out_ptr[u + 1] - out_ptr[u];
-      contrib_new[u] = od ? nw / (float)od : 0.f;
-      if (e != 0.0) atomicAdd(err, e);
-    }
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += sh[i];
+    partial[blockIdx.x] = v;
   }
+}
+
+__global__ void __launch_bounds__(256) pr_hub_final_kernel(const uint32_t* __restrict__ hubs, uint32_t n_hubs,
+                                                           const uint32_t* __restrict__ hub_chunk_ptr,
+                                                           const float* __restrict__ partial,
+                                                           const uint32_t* __restrict__ out_ptr, float base,
+                                                           float damping, float* __restrict__ contrib_new,
+                                                           float* __restrict__ scores, double* err) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (i < n_hubs) {
+    const uint32_t u = hubs[i];
+    float s = 0.f;
+    for (uint32_t c = hub_chunk_ptr[i]; c < hub_chunk_ptr[i + 1]; ++c) s += partial[c];
+    const float nw = base + damping * s;
+    e = (double)fabsf(nw - scores[u]);
+    scores[u] = nw;
+    const uint32_t od = out_ptr[u + 1] - out_ptr[u];
+    contrib_new[u] = od ? nw / (float)od : 0.f;
+  }
+  block_add_err(e, err);
 }
 
 // ---- SSSP ---------------------------------------------------------------------
@@ -424,7 +452,8 @@ using namespace cozo;
 
 extern "C" void cozo_gpu_graph_free(cozo_gpu_graph_t* g) {
   if (!g) return;
-  void* ptrs[] = {g->out_ptr, g->out_idx, g->in_ptr, g->in_idx, g->out_w, g->hubs, g->blk_start};
+  void* ptrs[] = {g->out_ptr,  g->out_idx,       g->in_ptr,    g->in_idx,   g->out_w,
+                  g->hubs,     g->blk_start,     g->hub_chunk_ptr, g->chunk_beg, g->chunk_end};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete g;
@@ -555,6 +584,23 @@ extern "C" int cozo_gpu_graph_stage(cozo_gpu_graph_t** out, uint32_t n, uint64_t
       G_CUDA(cudaMemcpy(g->blk_start, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice));
     G_CUDA(cudaMalloc(&g->hubs, std::max<size_t>(hubs.size(), 1) * 4));
     if (!hubs.empty()) G_CUDA(cudaMemcpy(g->hubs, hubs.data(), hubs.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> cptr(1, 0), cbeg, cend;
+    for (uint32_t hr : hubs) {
+      for (uint32_t b = hin[hr]; b < hin[hr + 1]; b += HUB_CHUNK) {
+        cbeg.push_back(b);
+        cend.push_back(std::min(b + HUB_CHUNK, hin[hr + 1]));
+      }
+      cptr.push_back((uint32_t)cbeg.size());
+    }
+    g->n_chunks = (uint32_t)cbeg.size();
+    G_CUDA(cudaMalloc(&g->hub_chunk_ptr, cptr.size() * 4));
+    G_CUDA(cudaMemcpy(g->hub_chunk_ptr, cptr.data(), cptr.size() * 4, cudaMemcpyHostToDevice));
+    G_CUDA(cudaMalloc(&g->chunk_beg, std::max<size_t>(cbeg.size(), 1) * 4));
+    G_CUDA(cudaMalloc(&g->chunk_end, std::max<size_t>(cbeg.size(), 1) * 4));
+    if (!cbeg.empty()) {
+      G_CUDA(cudaMemcpy(g->chunk_beg, cbeg.data(), cbeg.size() * 4, cudaMemcpyHostToDevice));
+      G_CUDA(cudaMemcpy(g->chunk_end, cend.data(), cend.size() * 4, cudaMemcpyHostToDevice));
+    }
   }
 #undef G_CUDA
   *out = g;
@@ -586,7 +632,8 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   const uint32_t n = g->n;
   if (n == 0) return 0;  // pagerank.rs:43-45
   const DeviceInfo& di = device_info();
-  DevBuf scores, c0, c1, err;
+  DevBuf scores, c0, c1, err, partial;
+  COZO_CUDA(cudaMalloc(&partial.p, (size_t)std::max(g->n_chunks, 1u) * 4));
   COZO_CUDA(cudaMalloc(&scores.p, (size_t)n * 4));
   COZO_CUDA(cudaMalloc(&c0.p, (size_t)n * 4));
   COZO_CUDA(cudaMalloc(&c1.p, (size_t)n * 4));
@@ -613,9 +660,12 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
     if (g->n_blk)
       pr_iter_kernel<<<grid, 256>>>(g->blk_start, g->n_blk, g->in_ptr, g->in_idx, g->out_ptr, base, damping, cold,
                                     cnew, scores.as<float>(), err.as<double>());
-    if (g->n_hubs)
-      pr_hub_kernel<<<g->n_hubs, 256>>>(g->hubs, g->in_ptr, g->in_idx, g->out_ptr, base, damping, cold, cnew,
-                                        scores.as<float>(), err.as<double>());
+    if (g->n_hubs) {
+      pr_hub_partial_kernel<<<g->n_chunks, 256>>>(g->chunk_beg, g->chunk_end, g->in_idx, cold, partial.as<float>());
+      pr_hub_final_kernel<<<(g->n_hubs + 255) / 256, 256>>>(g->hubs, g->n_hubs, g->hub_chunk_ptr, partial.as<float>(),
+                                                            g->out_ptr, base, damping, cnew, scores.as<float>(),
+                                                            err.as<double>());
+    }
     cudaError_t ce = cudaMemcpy(&herr, err.p, 8, cudaMemcpyDeviceToHost);
     if (ce != cudaSuccess) {
       ret = set_error(COZO_GPU_ECUDA, "pagerank iteration failed: %s", cudaGetErrorString(ce));

@@ -148,6 +148,9 @@ static KernelFn pick_kernel(uint32_t ld, int metric, bool bulk) {
   return pick_nv<4>(need, metric, bulk);
 }
 
+static HnswWorkspace* new_ws();
+void hnsw_prewarm_pool(cozo_gpu_hnsw* h, size_t vis_words, size_t vlog_words);
+
 int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words) {
   if (ws->vis_words < vis_words) {
     if (ws->vis) cudaFree(ws->vis);
@@ -167,15 +170,32 @@ int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words) {
   return 0;
 }
 
+// Each in-flight search owns one workspace (visited bitmaps are n/8 bytes per resident warp).
+// At most "hnsw.max_workspaces" (default 3) exist per index; further callers wait for a
+// release instead of allocating hundreds of MB inside the hot path.
 HnswWorkspace* hnsw_acquire_ws(cozo_gpu_hnsw* h) {
   {
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::unique_lock<std::mutex> lk(h->mu);
+    const uint32_t cap = (uint32_t)std::max<int64_t>(1, get_option("hnsw.max_workspaces", 3));
+    h->cv.wait(lk, [&] { return !h->pool.empty() || h->n_workspaces < cap; });
     if (!h->pool.empty()) {
       HnswWorkspace* ws = h->pool.back();
       h->pool.pop_back();
       return ws;
     }
+    h->n_workspaces++;
   }
+  HnswWorkspace* ws = new_ws();
+  if (!ws) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->n_workspaces--;
+    h->cv.notify_one();
+    return nullptr;
+  }
+  return ws;
+}
+
+static HnswWorkspace* new_ws() {
   auto* ws = new HnswWorkspace();
   if (cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ws->e0) != cudaSuccess || cudaEventCreate(&ws->e1) != cudaSuccess ||
@@ -187,9 +207,35 @@ HnswWorkspace* hnsw_acquire_ws(cozo_gpu_hnsw* h) {
   return ws;
 }
 
+// Create the remaining workspaces of the pool with the sizes the first search needed, so that
+// back-to-back asynchronous calls never allocate (cudaMalloc/cudaMemset serialise the device).
+void hnsw_prewarm_pool(cozo_gpu_hnsw* h, size_t vis_words, size_t vlog_words) {
+  const uint32_t cap = (uint32_t)std::max<int64_t>(1, get_option("hnsw.max_workspaces", 3));
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> lk(h->mu);
+      if (h->n_workspaces >= cap) return;
+      h->n_workspaces++;
+    }
+    HnswWorkspace* ws = new_ws();
+    if (!ws || hnsw_ws_reserve(ws, vis_words, vlog_words) != 0) {
+      if (ws) hnsw_release_ws(h, ws);  // usable, just not pre-sized
+      else {
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->n_workspaces--;
+      }
+      return;
+    }
+    hnsw_release_ws(h, ws);
+  }
+}
+
 void hnsw_release_ws(cozo_gpu_hnsw* h, HnswWorkspace* ws) {
-  std::lock_guard<std::mutex> lk(h->mu);
-  h->pool.push_back(ws);
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->pool.push_back(ws);
+  }
+  h->cv.notify_one();
 }
 
 static void free_ws(HnswWorkspace* ws) {
@@ -254,6 +300,7 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
   size_t slots = (size_t)grid * wpc;
   int rc = hnsw_ws_reserve(ws, slots * nwords, slots * logcap);
   if (rc) return rc;
+  hnsw_prewarm_pool(h, slots * nwords, slots * logcap);  // first call only: no allocation in later calls
 
   p.queries = d_q;
   p.B = B;

@@ -1,5 +1,6 @@
 // hnsw_host.hpp — host-side state of a staged HNSW index (opaque cozo_gpu_hnsw_t).
 #pragma once
+#include <condition_variable>
 #include <mutex>
 #include <vector>
 
@@ -44,7 +45,9 @@ struct cozo_gpu_hnsw {
   uint32_t n_levels = 1;
   uint32_t m_max0 = 0, m_max = 0;
   std::mutex mu;
+  std::condition_variable cv;
   std::vector<HnswWorkspace*> pool;
+  uint32_t n_workspaces = 0;  // created so far (bounded by the "hnsw.max_workspaces" option)
 };
 
 namespace cozo {

@@ -13,6 +13,6 @@ for st in 2 3 4 6 8; do for w in 2 4 8; do
   echo "== stages=$st wpc=$w"; timeout 300 python bench.py --steps 5 --warmup 2 --no-cpu --opt hnsw.stages=$st --opt hnsw.warps_per_cta=$w 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['frac'], d['ms_per_step'])"
 done; done > gpurun_out/sweep.txt 2>&1
 # 4. config 3: 10M x 768, ef=200, k=100, batch=65536
-timeout 1500 python bench.py --n 10000000 --batch 65536 --k 100 --steps 3 --warmup 1 --cpu-sample 256 > gpurun_out/bench_10m.json 2> gpurun_out/bench_10m.err
+timeout 1500 python bench.py --rows 10000000 --batch 65536 --k 100 --steps 3 --warmup 1 --cpu-sample 256 > gpurun_out/bench_10m.json 2> gpurun_out/bench_10m.err
 tail -c 3000 gpurun_out/bench_10m.json
 cat gpurun_out/sweep.txt
