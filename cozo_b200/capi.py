@@ -23,7 +23,7 @@ E_INVAL, E_CUDA, E_NODEV, E_NOMEM, E_KILLED, E_UNSUP = -1, -2, -3, -4, -5, -6
 EXPORTS = [
     "cozo_gpu_init", "cozo_gpu_shutdown", "cozo_gpu_last_error", "cozo_gpu_device_count", "cozo_gpu_set_option",
     "cozo_gpu_get_option", "cozo_gpu_hnsw_stage", "cozo_gpu_hnsw_free", "cozo_gpu_hnsw_search",
-    "cozo_gpu_hnsw_search_dev", "cozo_gpu_hnsw_build", "cozo_gpu_hnsw_info", "cozo_gpu_hnsw_level_size",
+    "cozo_gpu_hnsw_search_dev", "cozo_gpu_hnsw_search_scatter_dev", "cozo_gpu_hnsw_build", "cozo_gpu_hnsw_info", "cozo_gpu_hnsw_level_size",
     "cozo_gpu_hnsw_export_level", "cozo_gpu_hnsw_vectors_dev", "cozo_gpu_topk_merge_dev", "cozo_gpu_graph_stage",
     "cozo_gpu_graph_free", "cozo_gpu_graph_export", "cozo_gpu_pagerank", "cozo_gpu_sssp_multi", "cozo_gpu_closeness",
     "cozo_gpu_betweenness",
@@ -81,6 +81,7 @@ def load():
     L.cozo_gpu_hnsw_free.restype = None
     L.cozo_gpu_hnsw_search.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, C.POINTER(SearchStats)]
     L.cozo_gpu_hnsw_search_dev.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, vp]
+    L.cozo_gpu_hnsw_search_scatter_dev.argtypes = [vp, vp, u32, u32, u32, f64, u32, vp, vp, u32, vp, vp]
     L.cozo_gpu_hnsw_build.argtypes = [C.POINTER(vp), C.POINTER(HnswBuildDesc)]
     L.cozo_gpu_hnsw_info.argtypes = [vp, vp, vp, vp, vp]
     L.cozo_gpu_hnsw_level_size.argtypes = [vp, u32, vp, vp]
@@ -246,6 +247,15 @@ class HnswIndex:
                    qstats_ptr: int | None = None, stream: int | None = None, radius: float | None = None):
         _check(load().cozo_gpu_hnsw_search_dev(self._h, q_ptr, B, k, ef, -1.0 if radius is None else float(radius),
                                                ids_ptr, dist_ptr, count_ptr, qstats_ptr, stream))
+
+    def search_scatter_dev(self, q_ptr: int, B: int, k: int, ef: int, dest_ids_ptrs, dest_dist_ptrs, slot: int,
+                           qstats_ptr: int | None = None, stream: int | None = None, radius: float | None = None):
+        """fused search + exchange: top-k lists go straight into every destination's [S][B][k] buffers"""
+        n = len(dest_ids_ptrs)
+        ia = (C.c_uint64 * n)(*[int(x) for x in dest_ids_ptrs])
+        da = (C.c_uint64 * n)(*[int(x) for x in dest_dist_ptrs])
+        _check(load().cozo_gpu_hnsw_search_scatter_dev(self._h, q_ptr, B, k, ef, -1.0 if radius is None else float(radius),
+                                                       n, ia, da, slot, qstats_ptr, stream))
 
     def close(self):
         if self._h:

@@ -26,6 +26,12 @@ struct SearchParams {
   uint32_t ns;
   uint32_t warp_smem;  // bytes of shared memory per warp
   uint32_t off_fi, off_pend, off_bars, off_ring;
+  // fused exchange of the sharded corpus: besides (or instead of) out_ids/out_dist the top-k of
+  // query qi is stored into every destination's [n_slots][B][k] gather buffer at slot `slot`;
+  // destinations are peer GPUs' buffers mapped over NVLink (plain st.global on peer pointers).
+  uint32_t n_dest, slot;
+  uint32_t* dest_ids[COZO_GPU_MAX_PEERS];
+  float* dest_dist[COZO_GPU_MAX_PEERS];
 };
 
 // One warp per query, persistent CTAs pulling query indices from a counter.
@@ -100,9 +106,18 @@ __global__ void __launch_bounds__(128, MINB) hnsw_search_kernel(HnswDev g, Searc
       }
     }
     for (uint32_t i = lane; i < p.k; i += 32) {
-      bool in = i < found;
-      p.out_ids[(size_t)qi * p.k + i] = in ? (w.fi[i] & IDMASK) : NONE;
-      p.out_dist[(size_t)qi * p.k + i] = in ? w.fd[i] : INFINITY;
+      const bool in = i < found;
+      const uint32_t oid = in ? (w.fi[i] & IDMASK) : NONE;
+      const float od = in ? w.fd[i] : INFINITY;
+      if (p.out_ids) {
+        p.out_ids[(size_t)qi * p.k + i] = oid;
+        p.out_dist[(size_t)qi * p.k + i] = od;
+      }
+      const size_t at = ((size_t)p.slot * p.B + qi) * p.k + i;
+      for (uint32_t d = 0; d < p.n_dest; ++d) {  // the all-gather, fused into the epilogue
+        p.dest_ids[d][at] = oid;
+        p.dest_dist[d][at] = od;
+      }
     }
     if (lane == 0) {
       if (p.out_count) p.out_count[qi] = found;
@@ -255,7 +270,7 @@ static void free_ws(HnswWorkspace* ws) {
 
 int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, uint32_t B, uint32_t k, uint32_t ef,
                        double radius, uint32_t* d_ids, float* d_dist, uint32_t* d_count, uint32_t* d_qstats,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const ScatterDest* scatter) {
   const DeviceInfo& di = device_info();
   const HnswDev& g = h->dev;
   if (B == 0) return 0;
@@ -318,6 +333,16 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
   p.vlog = ws->vlog;
   p.logcap = logcap;
   p.ns = ns;
+  p.n_dest = 0;
+  p.slot = 0;
+  if (scatter) {
+    p.n_dest = scatter->n_dest;
+    p.slot = scatter->slot;
+    for (uint32_t d = 0; d < scatter->n_dest; ++d) {
+      p.dest_ids[d] = scatter->ids[d];
+      p.dest_dist[d] = scatter->dist[d];
+    }
+  }
   COZO_CUDA(cudaMemsetAsync(ws->counter, 0, 4, stream));
   fn<<<grid, wpc * 32, smem, stream>>>(g, p);
   COZO_CUDA(cudaGetLastError());
@@ -489,16 +514,18 @@ static int check_search_args(cozo_gpu_hnsw_t* h, uint32_t k, uint32_t ef) {
   return 0;
 }
 
-extern "C" int cozo_gpu_hnsw_search_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k,
-                                        uint32_t ef, double radius, uint32_t* out_ids_dev, float* out_dist_dev,
-                                        uint32_t* out_count_dev, uint32_t* per_query_stats_dev, void* stream) {
+static int search_dev_impl(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k, uint32_t ef,
+                           double radius, uint32_t* out_ids_dev, float* out_dist_dev, uint32_t* out_count_dev,
+                           uint32_t* per_query_stats_dev, void* stream, const ScatterDest* scatter) {
   int rc = check_search_args(h, k, ef);
   if (rc) return rc;
-  if (B && (!queries_dev || !out_ids_dev || !out_dist_dev)) return set_error(COZO_GPU_EINVAL, "null buffer");
+  if (B && !queries_dev) return set_error(COZO_GPU_EINVAL, "null buffer");
+  if (B && !scatter && (!out_ids_dev || !out_dist_dev)) return set_error(COZO_GPU_EINVAL, "null buffer");
+  if ((out_ids_dev == nullptr) != (out_dist_dev == nullptr)) return set_error(COZO_GPU_EINVAL, "ids/dist must come together");
   HnswWorkspace* ws = hnsw_acquire_ws(h);
   if (!ws) return COZO_GPU_ECUDA;
   rc = hnsw_launch_search(h, ws, queries_dev, B, k, ef, radius, out_ids_dev, out_dist_dev, out_count_dev,
-                          per_query_stats_dev, (cudaStream_t)stream);
+                          per_query_stats_dev, (cudaStream_t)stream, scatter);
   // The workspace (visited bitmaps) stays in use until the kernel ends: hand it
   // back to the pool from a host callback ordered after the kernel on `stream`,
   // which keeps this call asynchronous.
@@ -526,6 +553,30 @@ extern "C" int cozo_gpu_hnsw_search_dev(cozo_gpu_hnsw_t* h, const float* queries
   }
   hnsw_release_ws(h, ws);
   return rc;
+}
+
+extern "C" int cozo_gpu_hnsw_search_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k,
+                                        uint32_t ef, double radius, uint32_t* out_ids_dev, float* out_dist_dev,
+                                        uint32_t* out_count_dev, uint32_t* per_query_stats_dev, void* stream) {
+  return search_dev_impl(h, queries_dev, B, k, ef, radius, out_ids_dev, out_dist_dev, out_count_dev,
+                         per_query_stats_dev, stream, nullptr);
+}
+
+extern "C" int cozo_gpu_hnsw_search_scatter_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k,
+                                                uint32_t ef, double radius, uint32_t n_dest,
+                                                const uint64_t* dest_ids_ptrs, const uint64_t* dest_dist_ptrs,
+                                                uint32_t slot, uint32_t* per_query_stats_dev, void* stream) {
+  if (n_dest == 0 || n_dest > COZO_GPU_MAX_PEERS || !dest_ids_ptrs || !dest_dist_ptrs)
+    return set_error(COZO_GPU_EINVAL, "n_dest must be in [1,%d]", COZO_GPU_MAX_PEERS);
+  ScatterDest sc{};
+  sc.n_dest = n_dest;
+  sc.slot = slot;
+  for (uint32_t d = 0; d < n_dest; ++d) {
+    sc.ids[d] = reinterpret_cast<uint32_t*>(dest_ids_ptrs[d]);
+    sc.dist[d] = reinterpret_cast<float*>(dest_dist_ptrs[d]);
+    if (!sc.ids[d] || !sc.dist[d]) return set_error(COZO_GPU_EINVAL, "null destination buffer");
+  }
+  return search_dev_impl(h, queries_dev, B, k, ef, radius, nullptr, nullptr, nullptr, per_query_stats_dev, stream, &sc);
 }
 
 extern "C" int cozo_gpu_hnsw_search(cozo_gpu_hnsw_t* h, const float* queries, uint32_t B, uint32_t k, uint32_t ef,
@@ -579,7 +630,7 @@ extern "C" int cozo_gpu_hnsw_search(cozo_gpu_hnsw_t* h, const float* queries, ui
   cudaStream_t st = ws->stream;
   S_CUDA(cudaMemcpyAsync(ws->q, queries, qf * 4, cudaMemcpyHostToDevice, st));
   S_CUDA(cudaEventRecord(ws->e0, st));
-  rc = hnsw_launch_search(h, ws, ws->q, B, k, ef, radius, ws->ids, ws->dist, ws->count, ws->qstats, st);
+  rc = hnsw_launch_search(h, ws, ws->q, B, k, ef, radius, ws->ids, ws->dist, ws->count, ws->qstats, st, nullptr);
   if (rc) return done(rc);
   S_CUDA(cudaEventRecord(ws->e1, st));
   S_CUDA(cudaMemcpyAsync(out_ids, ws->ids, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));

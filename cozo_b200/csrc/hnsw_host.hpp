@@ -51,9 +51,14 @@ struct cozo_gpu_hnsw {
 };
 
 namespace cozo {
+struct ScatterDest {
+  uint32_t n_dest, slot;
+  uint32_t* ids[COZO_GPU_MAX_PEERS];
+  float* dist[COZO_GPU_MAX_PEERS];
+};
 int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, uint32_t B, uint32_t k, uint32_t ef,
                        double radius, uint32_t* d_ids, float* d_dist, uint32_t* d_count, uint32_t* d_qstats,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const ScatterDest* scatter);
 HnswWorkspace* hnsw_acquire_ws(cozo_gpu_hnsw* h);
 void hnsw_release_ws(cozo_gpu_hnsw* h, HnswWorkspace* ws);
 int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words);

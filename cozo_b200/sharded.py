@@ -42,19 +42,68 @@ class ShardedTopK:
         return all_d, all_i
 
 
-class ShardedHnswSearch:
-    """Device path: local search -> all-gather -> merge kernel (CUDA only, no CPU fallback)."""
+class _PeerBuffers:
+    """[S,B,k] gather buffers in symmetric memory, double-buffered: every rank's search kernel
+    stores its lists straight into all peers' buffers over NVLink (fused exchange)."""
 
-    def __init__(self, index, local_rows: int, device: torch.device, group=None):
+    def __init__(self, world, B, k, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        gname = group.group_name if group is not None else dist.group.WORLD.group_name
+        if hasattr(symm_mem, "enable_symm_mem_for_group"):
+            try:
+                symm_mem.enable_symm_mem_for_group(gname)
+            except Exception:
+                pass
+        self.d, self.i, self.hd, self.hi = [], [], [], []
+        for _ in range(2):
+            td = symm_mem.empty((world, B, k), dtype=torch.float32, device=device)
+            ti = symm_mem.empty((world, B, k), dtype=torch.int32, device=device)
+            self.d.append(td)
+            self.i.append(ti)
+            self.hd.append(symm_mem.rendezvous(td, gname))
+            self.hi.append(symm_mem.rendezvous(ti, gname))
+        self.step = 0
+
+
+class ShardedHnswSearch:
+    """Device path (CUDA only, no CPU fallback).
+    exchange="nccl":  local search -> ONE NCCL all-gather per list -> merge kernel
+    exchange="fused": the search kernel's epilogue stores the lists into every peer's gather buffer
+                      (symmetric memory over NVLink), one device-side barrier, merge kernel."""
+
+    def __init__(self, index, local_rows: int, device: torch.device, group=None, exchange: str = "nccl"):
         from . import capi
         if device.type != "cuda":
             raise capi.CozoGpuError(capi.E_NODEV, "ShardedHnswSearch needs a CUDA device (no CPU fallback)")
         self.capi = capi
         self.index = index
+        self.group = group
         self.plumb = ShardedTopK(local_rows, device, group)
         self.device = device
+        self.exchange = exchange if self.plumb.world > 1 else "nccl"
+        self._peer = {}
+
+    def _search_fused(self, q_dev, k, ef, qstats):
+        B = q_dev.shape[0]
+        key = (B, k)
+        if key not in self._peer:
+            self._peer[key] = _PeerBuffers(self.plumb.world, B, k, self.device, self.group)
+        pb = self._peer[key]
+        s = pb.step & 1
+        pb.step += 1
+        stream = torch.cuda.current_stream().cuda_stream
+        self.index.search_scatter_dev(q_dev.data_ptr(), B, k, ef, pb.hi[s].buffer_ptrs, pb.hd[s].buffer_ptrs,
+                                      self.plumb.rank, None if qstats is None else qstats.data_ptr(), stream)
+        pb.hd[s].barrier(channel=s)      # all ranks' stores have landed (and step-2's merge is long done)
+        out_i = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        out_d = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        self.capi.topk_merge_dev(pb.d[s].data_ptr(), pb.i[s].data_ptr(), self.plumb.world, B, k,
+                                 self.plumb.offsets.data_ptr(), out_i.data_ptr(), out_d.data_ptr(), stream)
+        return out_i, out_d
 
     def search(self, q_dev: torch.Tensor, k: int, ef: int, qstats: torch.Tensor | None = None):
+        if self.exchange == "fused":
+            return self._search_fused(q_dev, k, ef, qstats)
         B = q_dev.shape[0]
         stream = torch.cuda.current_stream().cuda_stream
         ids = torch.empty((B, k), dtype=torch.int32, device=self.device)

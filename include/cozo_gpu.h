@@ -42,6 +42,7 @@ extern "C" {
 #define COZO_GPU_EUNSUP (-6)   /* outside the supported envelope (e.g. F64 vectors) */
 
 #define COZO_GPU_NONE 0xFFFFFFFFu /* padding id in result arrays */
+#define COZO_GPU_MAX_PEERS 16     /* destinations of the fused search + exchange */
 
 /* HnswDistance — parse/sys.rs:94-98; formulas hnsw.rs:66-109 */
 #define COZO_GPU_L2 0     /* sum (a-b)^2, squared, no sqrt      */
@@ -118,6 +119,17 @@ int cozo_gpu_hnsw_search(cozo_gpu_hnsw_t* h, const float* queries, uint32_t B, u
 int cozo_gpu_hnsw_search_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k, uint32_t ef,
                              double radius, uint32_t* out_ids_dev, float* out_dist_dev, uint32_t* out_count_dev,
                              uint32_t* per_query_stats_dev, void* stream);
+
+/* Sharded corpus, fused search + exchange: the search kernel stores the top-k of
+ * every query straight into the [n_slots][B][k] gather buffers of all `n_dest` destinations at
+ * slot `slot` (this rank) — peer GPUs' buffers mapped into this process over NVLink (CUDA IPC /
+ * symmetric memory; the pointers are passed as integers) — so the all-gather needs no separate
+ * collective.  The caller synchronises the ranks (any cross-GPU barrier) before merging with
+ * cozo_gpu_topk_merge_dev.  Padding as in cozo_gpu_hnsw_search. */
+int cozo_gpu_hnsw_search_scatter_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k,
+                                     uint32_t ef, double radius, uint32_t n_dest, const uint64_t* dest_ids_ptrs,
+                                     const uint64_t* dest_dist_ptrs, uint32_t slot, uint32_t* per_query_stats_dev,
+                                     void* stream);
 
 /* Index construction on the device (batched variant of hnsw_put_vector,
  * hnsw.rs:155-375: level law 46-52, ef_construction search 242-256, heuristic
