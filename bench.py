@@ -48,11 +48,11 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--m", type=int, default=16)
     ap.add_argument("--efc", type=int, default=200)
-    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("COZO_BENCH_CPU_SAMPLE", 1024)))
-    ap.add_argument("--ref-sample", type=int, default=int(os.environ.get("COZO_BENCH_REF_SAMPLE", 512)))
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("COZO_BENCH_CPU_SAMPLE", 4096)))
+    ap.add_argument("--ref-sample", type=int, default=int(os.environ.get("COZO_BENCH_REF_SAMPLE", 1024)))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value")
-    ap.add_argument("--exchange", default=os.environ.get("COZO_BENCH_EXCHANGE", "nccl"), choices=["nccl", "fused"],
+    ap.add_argument("--exchange", default=os.environ.get("COZO_BENCH_EXCHANGE", "fused"), choices=["nccl", "fused"],
                     help="N>1: one NCCL all-gather (north star) or peer stores fused into the search kernel")
     return ap.parse_args()
 
@@ -354,7 +354,7 @@ def main():
             "recall_at_k_vs_oracle": recall_vs_oracle,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": a.steps * (1 + (1 if world > 1 else 0)),
-            "exchange": (a.exchange if world > 1 else None),
+            "exchange": (sharded.exchange if world > 1 else None),
             "step_ms": step_ms,
         }
         print(json.dumps(line), flush=True)

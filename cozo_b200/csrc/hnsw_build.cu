@@ -172,6 +172,7 @@ __device__ __forceinline__ uint32_t heuristic_select(const HnswDev& g, const flo
       }
     }
     if (add) {
+      __syncwarp();  // all lanes have read cid[c] / sel_id[..] before lane 0 updates them
       if (lane == 0) {
         sel_id[ns] = id;
         sel_d[ns] = dq;

@@ -169,6 +169,7 @@ __device__ __forceinline__ void sorted_insert(WarpCtx& w, uint32_t ef, float d, 
     }
     __syncwarp();
   }
+  __syncwarp();  // every lane has finished reading fd[len-1] / the shifted slots (vote ops do not order memory)
   if (lane == 0) {
     w.fd[pos] = d;
     w.fi[pos] = id;

@@ -49,11 +49,6 @@ class _PeerBuffers:
     def __init__(self, world, B, k, device, group):
         import torch.distributed._symmetric_memory as symm_mem
         gname = group.group_name if group is not None else dist.group.WORLD.group_name
-        if hasattr(symm_mem, "enable_symm_mem_for_group"):
-            try:
-                symm_mem.enable_symm_mem_for_group(gname)
-            except Exception:
-                pass
         self.d, self.i, self.hd, self.hi = [], [], [], []
         for _ in range(2):
             td = symm_mem.empty((world, B, k), dtype=torch.float32, device=device)
@@ -87,7 +82,19 @@ class ShardedHnswSearch:
         B = q_dev.shape[0]
         key = (B, k)
         if key not in self._peer:
-            self._peer[key] = _PeerBuffers(self.plumb.world, B, k, self.device, self.group)
+            # symmetric memory needs every peer to be NVLink/P2P reachable; agree on the outcome
+            try:
+                pb = _PeerBuffers(self.plumb.world, B, k, self.device, self.group)
+                ok = 1
+            except Exception as e:  # pragma: no cover - depends on the box
+                pb, ok = None, 0
+                self.fallback_reason = repr(e)
+            t = torch.tensor([ok], device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            if int(t.item()) == 0:
+                self.exchange = "nccl"      # plain NCCL all-gather (the north-star exchange)
+                return self.search(q_dev, k, ef, qstats)
+            self._peer[key] = pb
         pb = self._peer[key]
         s = pb.step & 1
         pb.step += 1
