@@ -23,7 +23,7 @@ E_INVAL, E_CUDA, E_NODEV, E_NOMEM, E_KILLED, E_UNSUP = -1, -2, -3, -4, -5, -6
 EXPORTS = [
     "cozo_gpu_init", "cozo_gpu_shutdown", "cozo_gpu_last_error", "cozo_gpu_device_count", "cozo_gpu_set_option",
     "cozo_gpu_get_option", "cozo_gpu_hnsw_stage", "cozo_gpu_hnsw_free", "cozo_gpu_hnsw_search",
-    "cozo_gpu_hnsw_search_dev", "cozo_gpu_hnsw_search_scatter_dev", "cozo_gpu_hnsw_build", "cozo_gpu_hnsw_info", "cozo_gpu_hnsw_level_size",
+    "cozo_gpu_hnsw_search_dev", "cozo_gpu_hnsw_search_scatter_dev", "cozo_gpu_hnsw_build", "cozo_gpu_hnsw_insert", "cozo_gpu_hnsw_remove", "cozo_gpu_hnsw_info", "cozo_gpu_hnsw_level_size",
     "cozo_gpu_hnsw_export_level", "cozo_gpu_hnsw_vectors_dev", "cozo_gpu_topk_merge_dev", "cozo_gpu_graph_stage",
     "cozo_gpu_graph_free", "cozo_gpu_graph_export", "cozo_gpu_pagerank", "cozo_gpu_sssp_multi", "cozo_gpu_closeness",
     "cozo_gpu_betweenness",
@@ -83,6 +83,8 @@ def load():
     L.cozo_gpu_hnsw_search_dev.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, vp]
     L.cozo_gpu_hnsw_search_scatter_dev.argtypes = [vp, vp, u32, u32, u32, f64, u32, vp, vp, u32, vp, vp]
     L.cozo_gpu_hnsw_build.argtypes = [C.POINTER(vp), C.POINTER(HnswBuildDesc)]
+    L.cozo_gpu_hnsw_insert.argtypes = [vp, vp, u32, C.c_int32, u32, C.c_int32, vp]
+    L.cozo_gpu_hnsw_remove.argtypes = [vp, vp, u32]
     L.cozo_gpu_hnsw_info.argtypes = [vp, vp, vp, vp, vp]
     L.cozo_gpu_hnsw_level_size.argtypes = [vp, u32, vp, vp]
     L.cozo_gpu_hnsw_export_level.argtypes = [vp, u32, vp, vp, vp]
@@ -202,6 +204,18 @@ class HnswIndex:
         h = C.c_void_p()
         _check(L.cozo_gpu_hnsw_build(C.byref(h), C.byref(d)))
         return cls(h, d.dim, keep)
+
+    def insert(self, vectors: np.ndarray, ef_construction: int = 0, keep_pruned_connections: int = -1) -> int:
+        """hnsw_put of new rows (ids appended); returns the first new id"""
+        vectors = np.ascontiguousarray(vectors, np.float32).reshape(-1, self.dim)
+        first = C.c_uint32()
+        _check(load().cozo_gpu_hnsw_insert(self._h, _p(vectors), vectors.shape[0], 0, ef_construction,
+                                           keep_pruned_connections, C.byref(first)))
+        return first.value
+
+    def remove(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        _check(load().cozo_gpu_hnsw_remove(self._h, _p(ids), ids.size))
 
     def info(self):
         n, dim, nl, ep = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()

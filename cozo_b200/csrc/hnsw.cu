@@ -373,6 +373,8 @@ extern "C" int cozo_gpu_hnsw_stage(cozo_gpu_hnsw_t** out, const CozoGpuHnswStage
   h->n_levels = d->n_levels;
   h->m_max0 = d->m_max0;
   h->m_max = d->m_max;
+  h->live.assign(d->n_vectors, 1);
+  h->n_live = d->n_vectors;
   HnswDev& g = h->dev;
   g.n = n;
   g.dim = d->dim;
@@ -503,6 +505,10 @@ extern "C" void cozo_gpu_hnsw_free(cozo_gpu_hnsw_t* h) {
   if (h->d_adj0_dist) cudaFree(h->d_adj0_dist);
   if (h->d_adj_up_dist) cudaFree(h->d_adj_up_dist);
   if (h->d_node_level) cudaFree(h->d_node_level);
+  if (h->d_deg0) cudaFree(h->d_deg0);
+  if (h->d_deg_up) cudaFree(h->d_deg_up);
+  if (h->d_up_owner) cudaFree(h->d_up_owner);
+  if (h->d_dead) cudaFree(h->d_dead);
   delete h;
 }
 

@@ -40,6 +40,18 @@ struct cozo_gpu_hnsw {
   float* d_adj0_dist = nullptr;
   float* d_adj_up_dist = nullptr;
   uint8_t* d_node_level = nullptr;
+  uint32_t *d_deg0 = nullptr, *d_deg_up = nullptr;  // live out-degree of every row
+  uint32_t* d_up_owner = nullptr;                   // node owning each upper-layer row
+  uint8_t* d_dead = nullptr;                        // removed nodes (hnsw_remove)
+  uint32_t cap_n = 0;                               // allocated rows (>= dev.n); 0 = staged, exact fit
+  uint64_t cap_up = 0;
+  bool build_state_ready = false;
+  uint32_t ef_construction = 0;
+  int keep_pruned = 0;
+  uint64_t rng_state = 0x5EED0003ull;
+  uint32_t n_live = 0;
+  uint32_t borrowed_rows = 0;  // rows available in a borrowed vector buffer
+  std::vector<uint8_t> live;
   // host copies
   std::vector<uint8_t> node_level;  // top layer index of each node (0 = layer 0 only)
   uint32_t n_levels = 1;

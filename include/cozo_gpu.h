@@ -152,6 +152,17 @@ typedef struct {
 
 int cozo_gpu_hnsw_build(cozo_gpu_hnsw_t** out, const CozoGpuHnswBuildDesc* desc);
 
+/* Index maintenance on the device, for an index that was built here or staged from the host.
+ * insert = hnsw_put for rows whose keys sort after every indexed key (query/stored.rs:332 ->
+ * hnsw.rs:679-727): the vectors get the dense ids [n, n+count) (*first_id = n), levels from the
+ * handle's seeded level law; ef_construction 0 / keep_pruned < 0 keep the handle's settings
+ * (a staged index has none: pass them).  remove = hnsw_remove (hnsw.rs:728-868): the nodes'
+ * rows are deleted on every layer together with every edge that points at them; if the entry
+ * point goes, the first remaining row in key order takes over (hnsw.rs:828-865). */
+int cozo_gpu_hnsw_insert(cozo_gpu_hnsw_t* h, const float* vectors, uint32_t count, int32_t vectors_on_device,
+                         uint32_t ef_construction, int32_t keep_pruned_connections, uint32_t* first_id);
+int cozo_gpu_hnsw_remove(cozo_gpu_hnsw_t* h, const uint32_t* ids, uint32_t count);
+
 /* Read a staged / built index back as per-layer CSR (rows ascending by id). */
 int cozo_gpu_hnsw_info(cozo_gpu_hnsw_t* h, uint32_t* n_vectors, uint32_t* dim, uint32_t* n_levels,
                        uint32_t* entry_point);

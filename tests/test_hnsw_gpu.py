@@ -235,3 +235,72 @@ def test_search_dev_and_merge(gpu):
     exp_i = np.take_along_axis(cid, order, 1)
     assert np.array_equal(out_d.cpu().numpy(), exp_d)
     assert np.mean(out_i.cpu().numpy() == exp_i) > 0.999
+
+
+def _export_view(g, X, metric=O.L2):
+    ni, rp, ci, ep = g.export_levels()
+    return (ni, rp, ci, ep), O.OracleHnsw.from_levels(X, O.HnswLevels(ni, rp, ci, ep), metric=metric)
+
+
+def test_incremental_insert_and_remove(gpu):
+    """hnsw_put / hnsw_remove on the device (hnsw.rs:679-868): the maintained graph stays a valid
+    index, GPU search == oracle search on the exported graph, removed rows never come back."""
+    n0, n1, dim, m = 6000, 9000, 48, 12
+    X = uniform_vectors(n1, dim, 2024)
+    g = gpu.HnswIndex.build(X[:n0], m=m, ef_construction=80, level_seed=11)
+    first = g.insert(X[n0:n1])
+    assert first == n0 and g.info()[0] == n1
+    (ni, rp, ci, ep), view = _export_view(g, X)
+    deg0 = np.diff(rp[0].astype(np.int64))
+    assert deg0.max() <= 2 * m and deg0.min() >= 1
+    Q = uniform_vectors(300, dim, 2025)
+    out = g.search(Q, 10, 80)
+    ref = view.search(Q, 10, 80, n_threads=8)
+    _compare(out, ref, 10)
+    bi, _ = O.bruteforce_knn(X, Q, 10, n_threads=8)
+    full = gpu.HnswIndex.build(X, m=m, ef_construction=80, level_seed=11)
+    assert recall(out[0], bi) >= recall(full.search(Q, 10, 80)[0], bi) - 0.03     # as good as a one-shot build
+    assert (out[0] >= n0).mean() > 0.2                                             # new rows are found
+    # remove a third of the rows, including the entry point
+    rng = np.random.default_rng(5)
+    dead = np.unique(np.concatenate([rng.choice(n1, 3000, replace=False), [ep]])).astype(np.uint32)
+    g.remove(dead)
+    (ni, rp, ci, ep2), view = _export_view(g, X)
+    assert ep2 is not None and ep2 not in set(dead.tolist())
+    assert not np.isin(ci[0], dead).any()
+    for L in range(1, len(ci)):
+        assert not np.isin(ci[L], dead).any()
+    assert np.all(np.diff(rp[0].astype(np.int64))[dead] == 0)
+    out = g.search(Q, 10, 80)
+    assert not np.isin(out[0], dead).any()
+    ref = view.search(Q, 10, 80, n_threads=8)
+    _compare(out, ref, 10)
+    live = np.setdiff1d(np.arange(n1), dead)
+    bi, _ = O.bruteforce_knn(X[live], Q, 10, n_threads=8)
+    assert recall(out[0], live[bi.astype(np.int64)].astype(np.uint32)) > 0.75       # no repair, like the reference
+    # and rows can be added again after removals
+    g.insert(uniform_vectors(500, dim, 2026))
+    assert g.info()[0] == n1 + 500
+
+
+def test_insert_into_staged_index(gpu):
+    """an index staged from the host (no degrees / stored distances on the device) can be extended"""
+    n0, dim, m = 2500, 32, 8
+    X = uniform_vectors(n0 + 800, dim, 3030)
+    ix = O.OracleHnsw.new(n0, dim, m=m, ef_construction=50)
+    ix.insert_all(X[:n0])
+    g = _stage(gpu, X[:n0], ix.levels(), gpu.L2, m)
+    with pytest.raises(gpu.CozoGpuError):           # a staged index has no ef_construction until told
+        g.insert(X[n0:])
+    g.insert(X[n0:], ef_construction=50, keep_pruned_connections=0)
+    (_, rp, ci, ep), view = _export_view(g, X)
+    assert np.diff(rp[0].astype(np.int64)).max() <= 2 * m
+    Q = uniform_vectors(200, dim, 3031)
+    out = g.search(Q, 10, 60)
+    _compare(out, view.search(Q, 10, 60, n_threads=8), 10)
+    bi, _ = O.bruteforce_knn(X, Q, 10, n_threads=8)
+    assert recall(out[0], bi) > 0.85
+    # remove everything -> empty index
+    g.remove(np.arange(n0 + 800, dtype=np.uint32))
+    ids, _, cnt, _ = g.search(Q, 10, 60)
+    assert np.all(cnt == 0) and g.info()[3] is None
