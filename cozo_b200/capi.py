@@ -26,7 +26,7 @@ EXPORTS = [
     "cozo_gpu_hnsw_search_dev", "cozo_gpu_hnsw_search_scatter_dev", "cozo_gpu_hnsw_build", "cozo_gpu_hnsw_insert", "cozo_gpu_hnsw_remove", "cozo_gpu_hnsw_info", "cozo_gpu_hnsw_level_size",
     "cozo_gpu_hnsw_export_level", "cozo_gpu_hnsw_vectors_dev", "cozo_gpu_topk_merge_dev", "cozo_gpu_graph_stage",
     "cozo_gpu_graph_free", "cozo_gpu_graph_export", "cozo_gpu_pagerank", "cozo_gpu_sssp_multi", "cozo_gpu_closeness",
-    "cozo_gpu_betweenness",
+    "cozo_gpu_betweenness", "cozo_gpu_clustering",
 ]
 
 
@@ -99,6 +99,7 @@ def load():
     L.cozo_gpu_sssp_multi.argtypes = [vp, vp, u32, vp, vp, vp, vp]
     L.cozo_gpu_closeness.argtypes = [vp, vp, vp, vp]
     L.cozo_gpu_betweenness.argtypes = [vp, vp, vp, vp]
+    L.cozo_gpu_clustering.argtypes = [vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -337,6 +338,14 @@ class Graph:
         ms = C.c_double()
         _check(load().cozo_gpu_betweenness(self._h, _p(out), C.byref(ms), _p(poison)))
         return out, ms.value
+
+    def clustering(self, poison=None):
+        cc = np.zeros(self.n, np.float64)
+        nt = np.zeros(self.n, np.uint64)
+        deg = np.zeros(self.n, np.uint64)
+        ms = C.c_double()
+        _check(load().cozo_gpu_clustering(self._h, _p(cc), _p(nt), _p(deg), C.byref(ms), _p(poison)))
+        return cc, nt, deg, ms.value
 
     def close(self):
         if self._h:

@@ -428,6 +428,48 @@ __global__ void __launch_bounds__(256) betweenness_kernel(const uint32_t* __rest
     if (v != s && delta[v] != 0.0) atomicAdd(&bc[v], delta[v]);
 }
 
+// ClusteringCoefficients (fixed_rule/algos/triangles.rs:59-98): one warp per node u.  For every
+// position i of u's (sorted, duplicate-keeping) out-neighbour list the lanes sweep the positions j
+// whose value is smaller and test membership of that value in adj(edges[i]) by binary search.
+// Integer work: counts are exact, cc is the same f64 expression as the reference.
+__global__ void __launch_bounds__(256) clustering_kernel(const uint32_t* __restrict__ out_ptr,
+                                                         const uint32_t* __restrict__ out_idx, uint32_t n,
+                                                         double* __restrict__ cc,
+                                                         unsigned long long* __restrict__ n_tri,
+                                                         unsigned long long* __restrict__ degree) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= n) return;
+  const uint32_t b = out_ptr[u], e = out_ptr[u + 1];
+  const uint32_t deg = e - b;
+  unsigned long long t = 0;
+  if (deg >= 2) {
+    uint32_t lo_end = b;  // first position whose value is >= a (the list is sorted, a is non-decreasing in i)
+    for (uint32_t i = b; i < e; ++i) {
+      const uint32_t a = out_idx[i];
+      while (lo_end < e && out_idx[lo_end] < a) ++lo_end;
+      const uint32_t ab = out_ptr[a], ae = out_ptr[a + 1];
+      for (uint32_t j = b + lane; j < lo_end; j += 32) {
+        const uint32_t v = out_idx[j];
+        uint32_t lo = ab, hi = ae;
+        while (lo < hi) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (out_idx[mid] < v) lo = mid + 1;
+          else hi = mid;
+        }
+        t += (lo < ae && out_idx[lo] == v) ? 1ull : 0ull;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  if (lane == 0) {
+    degree[u] = deg;
+    n_tri[u] = t;
+    cc[u] = deg < 2 ? 0.0 : 2. * (double)t / ((double)deg * ((double)deg - 1.));
+  }
+}
+
 __global__ void f64_to_f32_kernel(const double* in, uint32_t n, float* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)in[i];
@@ -815,5 +857,38 @@ extern "C" int cozo_gpu_betweenness(cozo_gpu_graph_t* g, float* out, double* out
   if (rc) return rc;
   f64_to_f32_kernel<<<(n + 255) / 256, 256>>>(bc.as<double>(), n, bcf.as<float>());
   COZO_CUDA(cudaMemcpy(out, bcf.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int cozo_gpu_clustering(cozo_gpu_graph_t* g, double* out_cc, uint64_t* out_triangles, uint64_t* out_degree,
+                                   double* out_kernel_ms, const volatile int* poison) {
+  if (!g || !out_cc || !out_triangles || !out_degree) return set_error(COZO_GPU_EINVAL, "null argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (out_kernel_ms) *out_kernel_ms = 0;
+  const uint32_t n = g->n;
+  if (n == 0) return 0;
+  if (poisoned(poison)) return set_error(COZO_GPU_EKILLED, "Running query is killed before completion");
+  DevBuf cc, nt, dg;
+  COZO_CUDA(cudaMalloc(&cc.p, (size_t)n * 8));
+  COZO_CUDA(cudaMalloc(&nt.p, (size_t)n * 8));
+  COZO_CUDA(cudaMalloc(&dg.p, (size_t)n * 8));
+  cudaEvent_t e0, e1;
+  COZO_CUDA(cudaEventCreate(&e0));
+  COZO_CUDA(cudaEventCreate(&e1));
+  cudaEventRecord(e0);
+  clustering_kernel<<<(n + 7) / 8, 256>>>(g->out_ptr, g->out_idx, n, cc.as<double>(), nt.as<unsigned long long>(),
+                                          dg.as<unsigned long long>());
+  cudaEventRecord(e1);
+  cudaError_t ce = cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ce != cudaSuccess) return set_error(COZO_GPU_ECUDA, "clustering failed: %s", cudaGetErrorString(ce));
+  COZO_CUDA(cudaMemcpy(out_cc, cc.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  COZO_CUDA(cudaMemcpy(out_triangles, nt.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  COZO_CUDA(cudaMemcpy(out_degree, dg.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (out_kernel_ms) *out_kernel_ms = ms;
   return 0;
 }

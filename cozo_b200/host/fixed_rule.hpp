@@ -411,6 +411,24 @@ struct BetweennessCentrality : FixedRule {
   }
 };
 
+// ---- ClusteringCoefficients (fixed_rule/algos/triangles.rs:25-57) ------------------------------
+struct ClusteringCoefficients : FixedRule {
+  size_t arity(const Options&, const std::vector<std::string>&) const override { return 4; }
+  void run(const FixedRulePayload& payload, RegularTempStore& out, const Poison& poison) const override {
+    const auto& edges = payload.get_input(0);
+    StagedGraph g;
+    edges.as_directed_graph(true, g);  // always undirected, triangles.rs:35
+    const uint32_t n = g.node_count();
+    if (n == 0) return;
+    std::vector<double> cc(n);
+    std::vector<uint64_t> nt(n), deg(n);
+    gpu_check(cozo_gpu_clustering(g.g, cc.data(), nt.data(), deg.data(), nullptr, poison.raw()));
+    for (uint32_t idx = 0; idx < n; ++idx)  // triangles.rs:37-44
+      out.put({g.indices[idx], DataValue::from_float(cc[idx]), DataValue::from_int((int64_t)nt[idx]),
+               DataValue::from_int((int64_t)deg[idx])});
+  }
+};
+
 // ---- registry (fixed_rule/mod.rs:705-836; Db::register_fixed_rule runtime/db.rs:760-784) ---
 struct FixedRuleRegistry {
   std::map<std::string, std::shared_ptr<FixedRule>> rules;
@@ -420,6 +438,7 @@ struct FixedRuleRegistry {
     add_builtin("ShortestPathDijkstra", std::make_shared<ShortestPathDijkstra>());
     add_builtin("ClosenessCentrality", std::make_shared<ClosenessCentrality>());
     add_builtin("BetweennessCentrality", std::make_shared<BetweennessCentrality>());
+    add_builtin("ClusteringCoefficients", std::make_shared<ClusteringCoefficients>());
   }
   void add_builtin(const std::string& n, std::shared_ptr<FixedRule> r) {
     rules[n] = std::move(r);

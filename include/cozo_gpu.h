@@ -208,6 +208,11 @@ int cozo_gpu_sssp_multi(cozo_gpu_graph_t* g, const uint32_t* sources, uint32_t n
 int cozo_gpu_closeness(cozo_gpu_graph_t* g, float* out, double* out_kernel_ms, const volatile int* poison);
 int cozo_gpu_betweenness(cozo_gpu_graph_t* g, float* out, double* out_kernel_ms, const volatile int* poison);
 
+/* ClusteringCoefficients (fixed_rule/algos/triangles.rs:25-98) over the out-CSR of the MIRRORED
+ * edge stream (as_directed_graph(true), triangles.rs:35): per node (cc f64, n_triangles, degree). */
+int cozo_gpu_clustering(cozo_gpu_graph_t* g, double* out_cc, uint64_t* out_triangles, uint64_t* out_degree,
+                        double* out_kernel_ms, const volatile int* poison);
+
 #ifdef __cplusplus
 }
 #endif

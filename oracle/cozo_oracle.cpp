@@ -1170,6 +1170,39 @@ int orc_betweenness(void* gp, float* out, uint32_t n_threads, uint64_t path_cap)
   return 0;
 }
 
+// ClusteringCoefficients — fixed_rule/algos/triangles.rs:59-98 over the graph of
+// as_directed_graph(undirected = true) (triangles.rs:35).  `edges` is the out-neighbour list WITH
+// duplicates; a pair of positions (e_src, e_dst) counts when e_src > e_dst by value and e_dst
+// occurs among the out-neighbours of e_src.  The reference scans that list linearly; a binary
+// search over the sorted adjacency answers the same membership question.
+int orc_clustering(void* gp, double* cc, uint64_t* n_triangles, uint64_t* degree, uint32_t n_threads) {
+  const Csr& g = ((GraphHandle*)gp)->g;
+  parallel_for(g.n, n_threads, [&](uint32_t u, unsigned) {
+    const uint32_t* e = g.out_idx.data() + g.out_ptr[u];
+    const uint64_t deg = g.out_ptr[u + 1] - g.out_ptr[u];
+    degree[u] = deg;
+    if (deg < 2) {  // triangles.rs:72-73
+      cc[u] = 0.0;
+      n_triangles[u] = 0;
+      return;
+    }
+    uint64_t t = 0;
+    for (uint64_t i = 0; i < deg; ++i) {
+      const uint32_t a = e[i];
+      const uint32_t* ab = g.out_idx.data() + g.out_ptr[a];
+      const uint32_t* ae = g.out_idx.data() + g.out_ptr[a + 1];
+      for (uint64_t j = 0; j < deg; ++j) {
+        const uint32_t b = e[j];
+        if (a <= b) continue;  // triangles.rs:80-82
+        if (std::binary_search(ab, ae, b)) ++t;
+      }
+    }
+    n_triangles[u] = t;
+    cc[u] = 2. * (double)t / ((double)deg * ((double)deg - 1.));  // triangles.rs:93
+  });
+  return 0;
+}
+
 // seeded level law shared with tests (hnsw.rs:46-52 with a SplitMix64 uniform)
 int64_t orc_random_level(uint64_t* state, uint32_t m) {
   SplitMix64 r{*state};

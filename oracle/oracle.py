@@ -74,6 +74,8 @@ def lib():
         L.orc_closeness.argtypes = [vp, vp, u32]
         L.orc_betweenness.restype = C.c_int
         L.orc_betweenness.argtypes = [vp, vp, u32, u64]
+        L.orc_clustering.restype = C.c_int
+        L.orc_clustering.argtypes = [vp, vp, vp, vp, u32]
         L.orc_random_level.restype = i64
         L.orc_random_level.argtypes = [vp, u32]
         _lib = L
@@ -284,6 +286,14 @@ class OracleGraph:
         if rc != 0:
             raise RuntimeError("betweenness failed (zero-weight cycle)")
         return out
+
+    def clustering(self, n_threads=1):
+        """(cc f64, n_triangles u64, degree u64) per node; the graph must hold the mirrored edge stream"""
+        cc = np.zeros(self.n, np.float64)
+        nt = np.zeros(self.n, np.uint64)
+        deg = np.zeros(self.n, np.uint64)
+        lib().orc_clustering(self._h, _p(cc), _p(nt), _p(deg), n_threads)
+        return cc, nt, deg
 
     def close(self):
         if self._h:

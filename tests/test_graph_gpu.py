@@ -195,3 +195,25 @@ def test_air_routes_all_rules(gpu):
     gs, git, _, _ = g2.pagerank(0.85, 1e-4, 10)
     os_, oit, _ = o2.pagerank(0.85, 1e-4, 10)
     assert git == oit and np.max(np.abs(gs - os_) / os_) <= 1e-5
+
+
+def test_clustering_exact(gpu):
+    """ClusteringCoefficients: integer counts and the f64 coefficient are bit-identical to the oracle,
+    on a multigraph with duplicate edges and self loops (RMAT) and on the air-routes graph."""
+    from tests.test_air_routes_cpu import load_routes
+    n, src, dst = rmat_edges(12, 8, 99)
+    ms = np.concatenate([src, dst])       # mirrored stream, as as_directed_graph(true) emits it (per edge: f->t, t->f)
+    md = np.concatenate([dst, src])
+    g = gpu.Graph(n, ms, md)
+    o = O.OracleGraph(n, ms, md)
+    gc, gt, gd, _ = g.clustering()
+    oc, ot, od = o.clustering(n_threads=16)
+    assert np.array_equal(gt, ot) and np.array_equal(gd, od) and np.array_equal(gc, oc)
+    assert ot.max() > 100
+    n, src, dst, dist, _, _ = load_routes()
+    ms, md = np.concatenate([src, dst]), np.concatenate([dst, src])
+    g = gpu.Graph(n, ms, md)
+    o = O.OracleGraph(n, ms, md)
+    gc, gt, gd, ms_k = g.clustering()
+    oc, ot, od = o.clustering(n_threads=16)
+    assert np.array_equal(gt, ot) and np.array_equal(gd, od) and np.array_equal(gc, oc)

@@ -246,3 +246,13 @@ def test_hnsw_multi_vector_rows_and_empty_index(h):
     empty.stage(base, [[1, None, None, None, None, None, None, 0, b"c", False]],
                 {"dim": dim, "m": m, "ef_construction": 30, "fields": [1]})
     assert h.HnswSearchRA(base, empty, k=4, ef=30, bind_idx=0).iter([[Q[0]]]) == []
+
+
+def test_clustering_rule(h):
+    """?[node, cc, triangles, degree] <~ ClusteringCoefficients(*edges[]) (triangles.rs:25-57)"""
+    rows = [["a", "b"], ["b", "c"], ["c", "a"], ["c", "d"], ["d", "e"]]
+    out = h.Db().run_fixed_rule("ClusteringCoefficients", [rows], {}, head_arity=4)
+    got = {r[0]: (r[1], r[2], r[3]) for r in out}
+    assert got["a"] == (1.0, 1, 2) and got["b"] == (1.0, 1, 2)
+    assert got["c"] == (2.0 * 1 / (3 * 2), 1, 3) and got["d"] == (0.0, 0, 2) and got["e"] == (0.0, 0, 1)
+    assert [r[0] for r in out] == ["a", "b", "c", "d", "e"]

@@ -291,3 +291,27 @@ def test_frozen_oracle_outputs():
     sd, _ = g.sssp(np.arange(0, 200, 25, dtype=np.uint32))
     assert np.array_equal(sd, z["sssp"])
     assert np.array_equal(g.closeness(), z["closeness"]) and np.array_equal(g.betweenness(), z["betweenness"])
+
+
+def test_clustering_vs_networkx():
+    """ClusteringCoefficients (triangles.rs:25-98) on a simple undirected graph == networkx"""
+    import networkx as nx
+    rng = np.random.default_rng(17)
+    n = 150
+    pairs = {(int(a), int(b)) for a, b in zip(rng.integers(0, n, 900), rng.integers(0, n, 900)) if a < b}
+    src = np.array([p[0] for p in pairs] + [p[1] for p in pairs], np.uint32)     # mirrored (triangles.rs:35)
+    dst = np.array([p[1] for p in pairs] + [p[0] for p in pairs], np.uint32)
+    g = O.OracleGraph(n, src, dst)
+    cc, nt, deg = g.clustering(n_threads=4)
+    G = nx.Graph()
+    G.add_nodes_from(range(n))
+    G.add_edges_from(pairs)
+    tri, clu = nx.triangles(G), nx.clustering(G)
+    assert [int(x) for x in nt] == [tri[i] for i in range(n)]
+    assert [int(x) for x in deg] == [G.degree[i] for i in range(n)]
+    assert np.allclose(cc, [clu[i] for i in range(n)], rtol=1e-12, atol=0)
+    # duplicate edges count per position (multigraph), exactly as the position loops of triangles.rs:74-91
+    src2 = np.array([0, 1, 0, 2, 1, 2, 0, 1, 1, 0], np.uint32)
+    dst2 = np.array([1, 0, 2, 0, 2, 1, 1, 0, 0, 1], np.uint32)
+    cc2, nt2, deg2 = O.OracleGraph(3, src2, dst2).clustering()
+    assert deg2.tolist() == [4, 4, 2] and nt2.tolist() == [3, 3, 1]
