@@ -304,3 +304,30 @@ def test_insert_into_staged_index(gpu):
     g.remove(np.arange(n0 + 800, dtype=np.uint32))
     ids, _, cnt, _ = g.search(Q, 10, 60)
     assert np.all(cnt == 0) and g.info()[3] is None
+
+
+def test_concurrent_callers_share_one_index(gpu, cfg1):
+    """HnswSearchRA::iter runs on Rayon workers and independent queries run on their own threads
+    (query/eval.rs:199-202): the staged index is shared and search must be re-entrant."""
+    import threading
+    X, ix, g, Q = cfg1
+    expect = g.search(Q, 10, 64)[0]
+    results, errors = {}, []
+
+    def worker(t):
+        try:
+            for rep in range(6):
+                sl = slice(100 * t, 100 * t + 100)
+                ids, _, _, _ = g.search(Q[sl], 10, 64)
+                if not np.array_equal(ids, expect[sl]):
+                    errors.append((t, rep))
+            results[t] = True
+        except Exception as e:      # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors and len(results) == 8
