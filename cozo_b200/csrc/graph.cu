@@ -22,8 +22,10 @@ struct cozo_gpu_graph {
   float* out_w = nullptr;
   uint32_t* hubs = nullptr;  // rows with in-degree > HUB_T
   uint32_t n_hubs = 0;
-  uint32_t* blk_start = nullptr;  // [2*n_blk] row blocks [r0,r1) of the pull kernel (no hub row inside a block)
+  uint32_t* blk_start = nullptr;  // [2*n_blk] row mini-blocks [r0,r1) of the pull kernel (<=32 rows, <=256 in-edges)
   uint32_t n_blk = 0;
+  uint32_t* med_rows = nullptr;   // rows with BLK_CAP < in-degree <= HUB_T: one warp each
+  uint32_t n_med = 0;
   // hub rows are cut into chunks of <= HUB_CHUNK in-edges, one CTA per chunk
   uint32_t *hub_chunk_ptr = nullptr, *chunk_beg = nullptr, *chunk_end = nullptr;
   uint32_t n_chunks = 0;
@@ -31,9 +33,9 @@ struct cozo_gpu_graph {
 
 namespace cozo {
 
-constexpr uint32_t HUB_T = 1024;    // rows longer than this get a CTA of their own (tree sum)
-constexpr uint32_t BLK_CAP = 2048;  // in-edges staged in shared memory per row block
-constexpr uint32_t BLK_ROWS = 1024; // rows per block
+constexpr uint32_t HUB_T = 4096;   // rows longer than this are cut into HUB_CHUNK pieces, one CTA each
+constexpr uint32_t BLK_CAP = 256;  // in-edges of a warp's mini-block (8 gathers per lane in flight)
+constexpr uint32_t BLK_ROWS = 32;  // rows per mini-block: one lane sums one row
 constexpr uint32_t HUB_CHUNK = 4096; // in-edges of a hub row summed by one CTA
 
 __global__ void edge_check_kernel(const uint32_t* src, const uint32_t* dst, const float* w, uint64_t m, uint32_t n,
@@ -128,12 +130,13 @@ __device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t* a, uint64_t pol
   return v;
 }
 
-// CSR-stream pull: a CTA owns a block of consecutive rows with <= BLK_CAP in-edges in total.
-// Phase 1 streams the block's in_idx slice (coalesced, evict-first) and gathers contrib[v]
-// (4 independent gathers per thread in flight; contrib is 4N bytes and is asked to stay in L2)
-// into shared memory; phase 2 sums every row's slice IN IN-NEIGHBOUR ORDER with one thread,
-// which is the order `.sum::<f32>()` uses in graph::page_rank, so these rows match a
-// sequential CPU run bit for bit.
+// CSR-stream pull at warp granularity.  A warp owns a mini-block of <= 32 consecutive destination
+// rows with <= 256 in-edges in total.  Phase 1: the in_idx slice is read coalesced (L2 evict-first)
+// and every lane issues up to 8 independent gathers of contrib[v] (L2 evict-last: the 4N-byte
+// vector is asked to stay in L2) before the first use, staging the values in the warp's 1 KB of
+// shared memory; phase 2: lane l sums row l's slice IN IN-NEIGHBOUR ORDER, the order
+// `.sum::<f32>()` uses in graph::page_rank, so these rows match a sequential CPU run bit for bit.
+// No block-wide barrier anywhere: 64 independent warp pipelines per SM.
 __global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict__ blk_start, uint32_t n_blk,
                                                       const uint32_t* __restrict__ in_ptr,
                                                       const uint32_t* __restrict__ in_idx,
@@ -141,37 +144,82 @@ __global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict
                                                       const float* __restrict__ contrib_old,
                                                       float* __restrict__ contrib_new, float* __restrict__ scores,
                                                       double* err) {
-  __shared__ float vals[BLK_CAP];
+  __shared__ float vals_all[8][BLK_CAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* vals = vals_all[warp];
   const uint64_t keep = l2_policy_evict_last();
   const uint64_t stream = l2_policy_evict_first();
+  const uint32_t wglobal = blockIdx.x * 8 + warp, wtotal = gridDim.x * 8;
   double e = 0.0;
-  for (uint32_t blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
-    const uint32_t r0 = blk_start[2 * blk], r1 = blk_start[2 * blk + 1];  // [r0,r1) pairs
-    const uint32_t e0 = in_ptr[r0], e1 = in_ptr[r1];
-    uint32_t k = e0 + threadIdx.x;
-    for (; k + 768 < e1; k += 1024) {
-      uint32_t i0 = ldg_u32_hint(in_idx + k, stream), i1 = ldg_u32_hint(in_idx + k + 256, stream);
-      uint32_t i2 = ldg_u32_hint(in_idx + k + 512, stream), i3 = ldg_u32_hint(in_idx + k + 768, stream);
-      float v0 = ldg_f32_hint(contrib_old + i0, keep), v1 = ldg_f32_hint(contrib_old + i1, keep);
-      float v2 = ldg_f32_hint(contrib_old + i2, keep), v3 = ldg_f32_hint(contrib_old + i3, keep);
-      vals[k - e0] = v0;
-      vals[k - e0 + 256] = v1;
-      vals[k - e0 + 512] = v2;
-      vals[k - e0 + 768] = v3;
+  for (uint32_t blk = wglobal; blk < n_blk; blk += wtotal) {
+    const uint32_t r0 = blk_start[2 * blk], r1 = blk_start[2 * blk + 1];
+    const uint32_t nrows = r1 - r0;
+    uint32_t lo = 0, hi = 0;
+    if ((uint32_t)lane < nrows) {
+      lo = in_ptr[r0 + lane];
+      hi = in_ptr[r0 + lane + 1];
     }
-    for (; k < e1; k += 256) vals[k - e0] = ldg_f32_hint(contrib_old + ldg_u32_hint(in_idx + k, stream), keep);
-    __syncthreads();
-    for (uint32_t r = r0 + threadIdx.x; r < r1; r += 256) {
-      const uint32_t b = in_ptr[r] - e0, en = in_ptr[r + 1] - e0;
+    const uint32_t e0 = __shfl_sync(0xffffffffu, lo, 0);
+    const uint32_t e1 = __shfl_sync(0xffffffffu, hi, nrows - 1);
+    uint32_t idx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t k = e0 + lane + 32 * j;
+      idx[j] = k < e1 ? ldg_u32_hint(in_idx + k, stream) : NONE;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vals[lane + 32 * j] = idx[j] != NONE ? ldg_f32_hint(contrib_old + idx[j], keep) : 0.f;
+    __syncwarp();
+    if ((uint32_t)lane < nrows) {
+      const uint32_t r = r0 + lane;
       float s = 0.f;
-      for (uint32_t j = b; j < en; ++j) s += vals[j];
+      for (uint32_t j = lo - e0; j < hi - e0; ++j) s += vals[j];
       const float nw = base + damping * s;
       e += (double)fabsf(nw - scores[r]);
       scores[r] = nw;
       const uint32_t od = out_ptr[r + 1] - out_ptr[r];
       contrib_new[r] = od ? nw / (float)od : 0.f;
     }
-    __syncthreads();
+    __syncwarp();
+  }
+  block_add_err(e, err);
+}
+
+// rows with BLK_CAP < in-degree <= HUB_T: one warp per row, 4 gathers per lane in flight, shuffle tree
+__global__ void __launch_bounds__(256) pr_medium_kernel(const uint32_t* __restrict__ rows, uint32_t n_rows,
+                                                        const uint32_t* __restrict__ in_ptr,
+                                                        const uint32_t* __restrict__ in_idx,
+                                                        const uint32_t* __restrict__ out_ptr, float base,
+                                                        float damping, const float* __restrict__ contrib_old,
+                                                        float* __restrict__ contrib_new, float* __restrict__ scores,
+                                                        double* err) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const uint64_t keep = l2_policy_evict_last();
+  const uint64_t stream = l2_policy_evict_first();
+  double e = 0.0;
+  if (w < n_rows) {
+    const uint32_t r = rows[w];
+    const uint32_t b = in_ptr[r], en = in_ptr[r + 1];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    uint32_t k = b + lane;
+    for (; k + 96 < en; k += 128) {
+      uint32_t i0 = ldg_u32_hint(in_idx + k, stream), i1 = ldg_u32_hint(in_idx + k + 32, stream);
+      uint32_t i2 = ldg_u32_hint(in_idx + k + 64, stream), i3 = ldg_u32_hint(in_idx + k + 96, stream);
+      s0 += ldg_f32_hint(contrib_old + i0, keep);
+      s1 += ldg_f32_hint(contrib_old + i1, keep);
+      s2 += ldg_f32_hint(contrib_old + i2, keep);
+      s3 += ldg_f32_hint(contrib_old + i3, keep);
+    }
+    for (; k < en; k += 32) s0 += ldg_f32_hint(contrib_old + ldg_u32_hint(in_idx + k, stream), keep);
+    const float s = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) {
+      const float nw = base + damping * s;
+      e = (double)fabsf(nw - scores[r]);
+      scores[r] = nw;
+      const uint32_t od = out_ptr[r + 1] - out_ptr[r];
+      contrib_new[r] = od ? nw / (float)od : 0.f;
+    }
   }
   block_add_err(e, err);
 }
@@ -495,7 +543,8 @@ using namespace cozo;
 extern "C" void cozo_gpu_graph_free(cozo_gpu_graph_t* g) {
   if (!g) return;
   void* ptrs[] = {g->out_ptr,  g->out_idx,       g->in_ptr,    g->in_idx,   g->out_w,
-                  g->hubs,     g->blk_start,     g->hub_chunk_ptr, g->chunk_beg, g->chunk_end};
+                  g->hubs,     g->blk_start,     g->hub_chunk_ptr, g->chunk_beg, g->chunk_end,
+                  g->med_rows};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete g;
@@ -604,18 +653,26 @@ extern "C" int cozo_gpu_graph_stage(cozo_gpu_graph_t** out, uint32_t n, uint64_t
     // hub rows (in-degree > HUB_T) excluded and listed separately
     std::vector<uint32_t> hin(np1);
     G_CUDA(cudaMemcpy(hin.data(), g->in_ptr, np1 * 4, cudaMemcpyDeviceToHost));
-    std::vector<uint32_t> blocks, hubs;
+    std::vector<uint32_t> blocks, hubs, med;
     uint32_t r = 0;
     while (r < n) {
-      if (hin[r + 1] - hin[r] > HUB_T) {
+      const uint32_t d0 = hin[r + 1] - hin[r];
+      if (d0 > HUB_T) {
         hubs.push_back(r++);
         continue;
       }
+      if (d0 > BLK_CAP) {
+        med.push_back(r++);
+        continue;
+      }
       const uint32_t r0 = r;
-      while (r < n && r - r0 < BLK_ROWS && hin[r + 1] - hin[r] <= HUB_T && hin[r + 1] - hin[r0] <= BLK_CAP) ++r;
+      while (r < n && r - r0 < BLK_ROWS && hin[r + 1] - hin[r] <= BLK_CAP && hin[r + 1] - hin[r0] <= BLK_CAP) ++r;
       blocks.push_back(r0);
       blocks.push_back(r);
     }
+    g->n_med = (uint32_t)med.size();
+    G_CUDA(cudaMalloc(&g->med_rows, std::max<size_t>(med.size(), 1) * 4));
+    if (!med.empty()) G_CUDA(cudaMemcpy(g->med_rows, med.data(), med.size() * 4, cudaMemcpyHostToDevice));
     // blocks are [r0,r1) pairs; store starts and ends interleaved as consecutive pairs
     g->n_blk = (uint32_t)(blocks.size() / 2);
     g->n_hubs = (uint32_t)hubs.size();
@@ -691,7 +748,7 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   float* cnew = c1.as<float>();
   uint32_t iter = 0;
   double herr = 0;
-  const uint32_t grid = std::max(1u, std::min<uint32_t>(g->n_blk, (uint32_t)di.sm_count * 8 * 4));
+  const uint32_t grid = std::max(1u, std::min<uint32_t>((g->n_blk + 7) / 8, (uint32_t)di.sm_count * 8 * 4));
   int ret = 0;
   for (;;) {
     if (poisoned(poison)) {
@@ -702,6 +759,9 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
     if (g->n_blk)
       pr_iter_kernel<<<grid, 256>>>(g->blk_start, g->n_blk, g->in_ptr, g->in_idx, g->out_ptr, base, damping, cold,
                                     cnew, scores.as<float>(), err.as<double>());
+    if (g->n_med)
+      pr_medium_kernel<<<(g->n_med + 7) / 8, 256>>>(g->med_rows, g->n_med, g->in_ptr, g->in_idx, g->out_ptr, base,
+                                                     damping, cold, cnew, scores.as<float>(), err.as<double>());
     if (g->n_hubs) {
       pr_hub_partial_kernel<<<g->n_chunks, 256>>>(g->chunk_beg, g->chunk_end, g->in_idx, cold, partial.as<float>());
       pr_hub_final_kernel<<<(g->n_hubs + 255) / 256, 256>>>(g->hubs, g->n_hubs, g->hub_chunk_ptr, partial.as<float>(),
