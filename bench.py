@@ -238,14 +238,14 @@ def main():
         else:   # local search -> ONE all-gather per list -> merge kernel
             sharded.search(Qd[s], k, ef, qstats[s])
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()          # nvidia-smi needs a moment to start: launch it before the warm-up
     for s in range(a.warmup):
         step(s)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
+    time.sleep(0.3)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     torch.cuda.synchronize()
     t_start = time.perf_counter()

@@ -26,7 +26,7 @@ EXPORTS = [
     "cozo_gpu_hnsw_search_dev", "cozo_gpu_hnsw_search_scatter_dev", "cozo_gpu_hnsw_build", "cozo_gpu_hnsw_insert", "cozo_gpu_hnsw_remove", "cozo_gpu_hnsw_info", "cozo_gpu_hnsw_level_size",
     "cozo_gpu_hnsw_export_level", "cozo_gpu_hnsw_vectors_dev", "cozo_gpu_topk_merge_dev", "cozo_gpu_graph_stage",
     "cozo_gpu_graph_free", "cozo_gpu_graph_export", "cozo_gpu_pagerank", "cozo_gpu_sssp_multi", "cozo_gpu_closeness",
-    "cozo_gpu_betweenness", "cozo_gpu_clustering",
+    "cozo_gpu_betweenness", "cozo_gpu_clustering", "cozo_gpu_sssp_paths",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
     L.cozo_gpu_closeness.argtypes = [vp, vp, vp, vp]
     L.cozo_gpu_betweenness.argtypes = [vp, vp, vp, vp]
     L.cozo_gpu_clustering.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cozo_gpu_sssp_paths.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -338,6 +339,35 @@ class Graph:
         ms = C.c_double()
         _check(load().cozo_gpu_betweenness(self._h, _p(out), C.byref(ms), _p(poison)))
         return out, ms.value
+
+    def sssp_paths(self, sources, goals, forb_nodes=None, forb_edges=None, max_len=64, poison=None):
+        """batch of goal-directed searches; forb_nodes / forb_edges: per-search lists (or None).
+        -> list of (cost, path list) ; unreachable = (inf, [])"""
+        sources = np.ascontiguousarray(sources, np.uint32)
+        goals = np.ascontiguousarray(goals, np.uint32)
+        k = sources.size
+        fnp = fnn = fep = fes = fed = None
+        if forb_nodes is not None or forb_edges is not None:
+            forb_nodes = forb_nodes or [[] for _ in range(k)]
+            forb_edges = forb_edges or [[] for _ in range(k)]
+            fnp = np.zeros(k + 1, np.uint32)
+            fep = np.zeros(k + 1, np.uint32)
+            fnp[1:] = np.cumsum([len(x) for x in forb_nodes])
+            fep[1:] = np.cumsum([len(x) for x in forb_edges])
+            fnn = np.array([v for x in forb_nodes for v in x] or [0], np.uint32)
+            fes = np.array([e[0] for x in forb_edges for e in x] or [0], np.uint32)
+            fed = np.array([e[1] for x in forb_edges for e in x] or [0], np.uint32)
+        while True:
+            cost = np.zeros(k, np.float32)
+            ln = np.zeros(k, np.uint32)
+            paths = np.zeros((k, max_len), np.uint32)
+            ms = C.c_double()
+            _check(load().cozo_gpu_sssp_paths(self._h, _p(sources), _p(goals), k, _p(fnp), _p(fnn), _p(fep), _p(fes),
+                                              _p(fed), max_len, _p(cost), _p(ln), _p(paths), C.byref(ms), _p(poison)))
+            if k == 0 or ln.max() <= max_len:
+                break
+            max_len = int(ln.max())
+        return [(float(cost[i]), paths[i, :ln[i]].tolist()) for i in range(k)], ms.value
 
     def clustering(self, poison=None):
         cc = np.zeros(self.n, np.float64)

@@ -288,13 +288,28 @@ __global__ void __launch_bounds__(256) pr_hub_final_kernel(const uint32_t* __res
 // predecessors always form a tree.
 constexpr unsigned long long SSSP_INF = 0x7F800000FFFFFFFFull;  // (+inf, NONE)
 
+// ForbiddenNode / ForbiddenEdge sets (shortest_path_dijkstra.rs:188-218) of source `si` are the
+// slices [fn_ptr[si], fn_ptr[si+1]) of fn_nodes and [fe_ptr[si], fe_ptr[si+1]) of (fe_src, fe_dst);
+// they are a handful of entries (KShortestPathYen: one root path + at most k edges).
+struct ForbiddenSets {
+  const uint32_t *fn_ptr, *fn_nodes, *fe_ptr, *fe_src, *fe_dst;
+};
+
+template <bool FORB>
 __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ out_ptr,
                                                    const uint32_t* __restrict__ out_idx,
                                                    const float* __restrict__ out_w, uint32_t n,
                                                    const uint32_t* __restrict__ sources, uint32_t n_src,
-                                                   unsigned long long* state, uint32_t* flags) {
+                                                   unsigned long long* state, uint32_t* flags, ForbiddenSets fs) {
   const uint32_t si = blockIdx.x;
   if (si >= n_src) return;
+  uint32_t fnb = 0, fne = 0, feb = 0, fee = 0;
+  if (FORB) {
+    fnb = fs.fn_ptr[si];
+    fne = fs.fn_ptr[si + 1];
+    feb = fs.fe_ptr[si];
+    fee = fs.fe_ptr[si + 1];
+  }
   unsigned long long* st = state + (size_t)si * n;
   uint32_t* cur = flags + (size_t)si * 2 * n;
   uint32_t* nxt = cur + n;
@@ -320,6 +335,12 @@ __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ 
       const float du = __uint_as_float((uint32_t)(st[u] >> 32));
       for (uint32_t k = out_ptr[u]; k < out_ptr[u + 1]; ++k) {
         const uint32_t v = out_idx[k];
+        if (FORB) {  // shortest_path_dijkstra.rs:298-303
+          bool skip = false;
+          for (uint32_t f = fnb; f < fne; ++f) skip |= fs.fn_nodes[f] == v;
+          for (uint32_t f = feb; f < fee; ++f) skip |= (fs.fe_src[f] == u) & (fs.fe_dst[f] == v);
+          if (skip) continue;
+        }
         const float nd = du + (out_w ? out_w[k] : 1.0f);
         unsigned long long old = st[v];
         while (nd < __uint_as_float((uint32_t)(old >> 32))) {
@@ -341,6 +362,35 @@ __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ 
     uint32_t* t = cur;
     cur = nxt;
     nxt = t;
+  }
+}
+
+// goal-directed read-out (shortest_path_dijkstra.rs:318-336): walk the predecessors from the goal
+__global__ void sssp_path_kernel(const unsigned long long* state, uint32_t n, const uint32_t* sources,
+                                 const uint32_t* goals, uint32_t n_src, uint32_t max_len, float* cost, uint32_t* len,
+                                 uint32_t* paths) {
+  const uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+  if (si >= n_src) return;
+  const unsigned long long* st = state + (size_t)si * n;
+  const uint32_t s = sources[si], t = goals[si];
+  const float c = __uint_as_float((uint32_t)(st[t] >> 32));
+  cost[si] = c;
+  if (!isfinite(c)) {  // (target, inf, [])
+    len[si] = 0;
+    return;
+  }
+  uint32_t cnt = 1, cur = t;
+  while (cur != s && cnt <= n) {
+    cur = (uint32_t)(st[cur] & 0xFFFFFFFFull);
+    ++cnt;
+  }
+  len[si] = cnt;
+  if (cnt > max_len) return;  // caller sees len > max_len and retries with a larger buffer
+  uint32_t* p = paths + (size_t)si * max_len;
+  cur = t;
+  for (uint32_t i = cnt; i-- > 0;) {
+    p[i] = cur;
+    cur = (uint32_t)(st[cur] & 0xFFFFFFFFull);
   }
 }
 
@@ -818,8 +868,8 @@ static int sssp_chunks(cozo_gpu_graph_t* g, const uint32_t* sources_host, uint32
     }
     uint32_t c = std::min(chunk, n_src - s0);
     cudaMemcpy(dsrc.p, sources_host + s0, (size_t)c * 4, cudaMemcpyHostToDevice);
-    sssp_kernel<<<c, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc.as<uint32_t>(), c,
-                            state.as<unsigned long long>(), flags.as<uint32_t>());
+    sssp_kernel<false><<<c, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc.as<uint32_t>(), c,
+                                   state.as<unsigned long long>(), flags.as<uint32_t>(), ForbiddenSets{});
     ret = per_chunk(s0, c, state.as<unsigned long long>(), dsrc.as<uint32_t>());
     cudaError_t ce = cudaDeviceSynchronize();
     if (!ret && ce != cudaSuccess) ret = set_error(COZO_GPU_ECUDA, "sssp failed: %s", cudaGetErrorString(ce));
@@ -949,6 +999,78 @@ extern "C" int cozo_gpu_clustering(cozo_gpu_graph_t* g, double* out_cc, uint64_t
   COZO_CUDA(cudaMemcpy(out_cc, cc.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
   COZO_CUDA(cudaMemcpy(out_triangles, nt.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
   COZO_CUDA(cudaMemcpy(out_degree, dg.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (out_kernel_ms) *out_kernel_ms = ms;
+  return 0;
+}
+
+extern "C" int cozo_gpu_sssp_paths(cozo_gpu_graph_t* g, const uint32_t* sources, const uint32_t* goals, uint32_t n_src,
+                                   const uint32_t* forb_node_ptr, const uint32_t* forb_nodes,
+                                   const uint32_t* forb_edge_ptr, const uint32_t* forb_edge_src,
+                                   const uint32_t* forb_edge_dst, uint32_t max_len, float* out_cost, uint32_t* out_len,
+                                   uint32_t* out_paths, double* out_kernel_ms, const volatile int* poison) {
+  if (!g || (n_src && (!sources || !goals || !out_cost || !out_len || !out_paths)))
+    return set_error(COZO_GPU_EINVAL, "null argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (out_kernel_ms) *out_kernel_ms = 0;
+  const uint32_t n = g->n;
+  if (n_src == 0 || n == 0) return 0;
+  if (max_len == 0) return set_error(COZO_GPU_EINVAL, "max_len must be positive");
+  for (uint32_t i = 0; i < n_src; ++i)
+    if (sources[i] >= n || goals[i] >= n) return set_error(COZO_GPU_EINVAL, "source/goal out of range");
+  if (poisoned(poison)) return set_error(COZO_GPU_EKILLED, "Running query is killed before completion");
+  const bool forb = forb_node_ptr && forb_edge_ptr;
+  const uint32_t n_fn = forb ? forb_node_ptr[n_src] : 0, n_fe = forb ? forb_edge_ptr[n_src] : 0;
+  DevBuf state, flags, dsrc, dgoal, fnp, fnn, fep, fes, fed, dc, dl, dp;
+  COZO_CUDA(cudaMalloc(&state.p, (size_t)n_src * n * 8));
+  COZO_CUDA(cudaMalloc(&flags.p, (size_t)n_src * n * 8));
+  COZO_CUDA(cudaMalloc(&dsrc.p, (size_t)n_src * 4));
+  COZO_CUDA(cudaMalloc(&dgoal.p, (size_t)n_src * 4));
+  COZO_CUDA(cudaMalloc(&dc.p, (size_t)n_src * 4));
+  COZO_CUDA(cudaMalloc(&dl.p, (size_t)n_src * 4));
+  COZO_CUDA(cudaMalloc(&dp.p, (size_t)n_src * max_len * 4));
+  COZO_CUDA(cudaMemcpy(dsrc.p, sources, (size_t)n_src * 4, cudaMemcpyHostToDevice));
+  COZO_CUDA(cudaMemcpy(dgoal.p, goals, (size_t)n_src * 4, cudaMemcpyHostToDevice));
+  ForbiddenSets fs{};
+  if (forb) {
+    COZO_CUDA(cudaMalloc(&fnp.p, ((size_t)n_src + 1) * 4));
+    COZO_CUDA(cudaMalloc(&fep.p, ((size_t)n_src + 1) * 4));
+    COZO_CUDA(cudaMalloc(&fnn.p, std::max<size_t>(n_fn, 1) * 4));
+    COZO_CUDA(cudaMalloc(&fes.p, std::max<size_t>(n_fe, 1) * 4));
+    COZO_CUDA(cudaMalloc(&fed.p, std::max<size_t>(n_fe, 1) * 4));
+    COZO_CUDA(cudaMemcpy(fnp.p, forb_node_ptr, ((size_t)n_src + 1) * 4, cudaMemcpyHostToDevice));
+    COZO_CUDA(cudaMemcpy(fep.p, forb_edge_ptr, ((size_t)n_src + 1) * 4, cudaMemcpyHostToDevice));
+    if (n_fn) COZO_CUDA(cudaMemcpy(fnn.p, forb_nodes, (size_t)n_fn * 4, cudaMemcpyHostToDevice));
+    if (n_fe) {
+      COZO_CUDA(cudaMemcpy(fes.p, forb_edge_src, (size_t)n_fe * 4, cudaMemcpyHostToDevice));
+      COZO_CUDA(cudaMemcpy(fed.p, forb_edge_dst, (size_t)n_fe * 4, cudaMemcpyHostToDevice));
+    }
+    fs = ForbiddenSets{fnp.as<uint32_t>(), fnn.as<uint32_t>(), fep.as<uint32_t>(), fes.as<uint32_t>(),
+                       fed.as<uint32_t>()};
+  }
+  cudaEvent_t e0, e1;
+  COZO_CUDA(cudaEventCreate(&e0));
+  COZO_CUDA(cudaEventCreate(&e1));
+  cudaEventRecord(e0);
+  if (forb)
+    sssp_kernel<true><<<n_src, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc.as<uint32_t>(), n_src,
+                                      state.as<unsigned long long>(), flags.as<uint32_t>(), fs);
+  else
+    sssp_kernel<false><<<n_src, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc.as<uint32_t>(), n_src,
+                                       state.as<unsigned long long>(), flags.as<uint32_t>(), fs);
+  sssp_path_kernel<<<(n_src + 127) / 128, 128>>>(state.as<unsigned long long>(), n, dsrc.as<uint32_t>(),
+                                                 dgoal.as<uint32_t>(), n_src, max_len, dc.as<float>(),
+                                                 dl.as<uint32_t>(), dp.as<uint32_t>());
+  cudaEventRecord(e1);
+  cudaError_t ce = cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ce != cudaSuccess) return set_error(COZO_GPU_ECUDA, "sssp_paths failed: %s", cudaGetErrorString(ce));
+  COZO_CUDA(cudaMemcpy(out_cost, dc.p, (size_t)n_src * 4, cudaMemcpyDeviceToHost));
+  COZO_CUDA(cudaMemcpy(out_len, dl.p, (size_t)n_src * 4, cudaMemcpyDeviceToHost));
+  COZO_CUDA(cudaMemcpy(out_paths, dp.p, (size_t)n_src * max_len * 4, cudaMemcpyDeviceToHost));
   if (out_kernel_ms) *out_kernel_ms = ms;
   return 0;
 }

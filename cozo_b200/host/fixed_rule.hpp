@@ -429,6 +429,168 @@ struct ClusteringCoefficients : FixedRule {
   }
 };
 
+// ---- KShortestPathYen (fixed_rule/algos/yen.rs:26-211) ------------------------------------------
+// The control flow of k_shortest_path_yen is the reference's; what changes is that the dijkstra
+// calls of one round — every spur node of every (start, goal) pair, which the reference runs one
+// after another (pairs in parallel via par_bridge, yen.rs:85) — go to the device as ONE batch of
+// goal-directed searches with their ForbiddenEdge / ForbiddenNode sets (cozo_gpu_sssp_paths).
+struct KShortestPathYen : FixedRule {
+  size_t arity(const Options&, const std::vector<std::string>&) const override { return 4; }
+
+  struct PairState {
+    uint32_t start, goal;
+    std::vector<std::pair<float, std::vector<uint32_t>>> k_shortest, candidates;
+    bool done = false;
+  };
+  struct Search {
+    size_t pair;
+    size_t i;  // spur index, or SIZE_MAX for the initial search
+    uint32_t from;
+    std::vector<uint32_t> fn;
+    std::vector<std::pair<uint32_t, uint32_t>> fe;
+  };
+
+  static void run_batch(const StagedGraph& g, const std::vector<PairState>& ps, const std::vector<Search>& batch,
+                        std::vector<std::pair<float, std::vector<uint32_t>>>& res, const Poison& poison) {
+    const uint32_t k = (uint32_t)batch.size();
+    res.assign(k, {});
+    if (!k) return;
+    std::vector<uint32_t> src(k), goal(k), fnp(k + 1, 0), fep(k + 1, 0), fnn, fes, fed;
+    for (uint32_t b = 0; b < k; ++b) {
+      src[b] = batch[b].from;
+      goal[b] = ps[batch[b].pair].goal;
+      for (uint32_t v : batch[b].fn) fnn.push_back(v);
+      for (auto& e : batch[b].fe) {
+        fes.push_back(e.first);
+        fed.push_back(e.second);
+      }
+      fnp[b + 1] = (uint32_t)fnn.size();
+      fep[b + 1] = (uint32_t)fes.size();
+    }
+    if (fnn.empty()) fnn.push_back(0);
+    if (fes.empty()) {
+      fes.push_back(0);
+      fed.push_back(0);
+    }
+    uint32_t max_len = 64;
+    for (;;) {
+      std::vector<float> cost(k);
+      std::vector<uint32_t> len(k), paths((size_t)k * max_len);
+      gpu_check(cozo_gpu_sssp_paths(g.g, src.data(), goal.data(), k, fnp.data(), fnn.data(), fep.data(), fes.data(),
+                                    fed.data(), max_len, cost.data(), len.data(), paths.data(), nullptr, poison.raw()));
+      uint32_t need = 0;
+      for (uint32_t b = 0; b < k; ++b) need = std::max(need, len[b]);
+      if (need > max_len) {
+        max_len = need;
+        continue;
+      }
+      for (uint32_t b = 0; b < k; ++b)
+        res[b] = {cost[b], std::vector<uint32_t>(paths.begin() + (size_t)b * max_len,
+                                                 paths.begin() + (size_t)b * max_len + len[b])};
+      return;
+    }
+  }
+
+  void run(const FixedRulePayload& payload, RegularTempStore& out, const Poison& poison) const override {
+    const auto& edges = payload.get_input(0);
+    const auto& starting = payload.get_input(1);
+    const auto& termination = payload.get_input(2);
+    const bool f = false;
+    bool undirected = payload.bool_option("undirected", &f);  // yen.rs:38
+    size_t k = payload.pos_integer_option("k", nullptr);      // yen.rs:39 (required)
+    StagedGraph g;
+    edges.as_directed_weighted_graph(undirected, false, g);
+    std::set<uint32_t> starts, goals;  // BTreeSets, yen.rs:43-58
+    for (const Tuple& t : starting.iter())
+      if (!t.empty()) {
+        auto it = g.inv_indices.find(t[0]);
+        if (it != g.inv_indices.end()) starts.insert(it->second);
+      }
+    for (const Tuple& t : termination.iter())
+      if (!t.empty()) {
+        auto it = g.inv_indices.find(t[0]);
+        if (it != g.inv_indices.end()) goals.insert(it->second);
+      }
+    std::vector<PairState> ps;
+    for (uint32_t s0 : starts)
+      for (uint32_t g0 : goals) {
+        PairState p;
+        p.start = s0;
+        p.goal = g0;
+        ps.push_back(std::move(p));
+      }
+    if (ps.empty()) return;
+    // first edge s->d in adjacency order supplies the root-path cost (yen.rs:171-183)
+    std::map<std::pair<uint32_t, uint32_t>, float> first_edge;
+    for (size_t e = 0; e < g.src.size(); ++e) first_edge.emplace(std::make_pair(g.src[e], g.dst[e]), g.w[e]);
+
+    std::vector<Search> batch;
+    std::vector<std::pair<float, std::vector<uint32_t>>> res;
+    for (size_t pi = 0; pi < ps.size(); ++pi) batch.push_back({pi, SIZE_MAX, ps[pi].start, {}, {}});
+    run_batch(g, ps, batch, res, poison);
+    for (size_t b = 0; b < batch.size(); ++b) ps[batch[b].pair].k_shortest.push_back(res[b]);  // yen.rs:130-136
+
+    for (size_t it = 1; it < k; ++it) {  // yen.rs:138
+      batch.clear();
+      for (size_t pi = 0; pi < ps.size(); ++pi) {
+        PairState& p = ps[pi];
+        if (p.done) continue;
+        const std::vector<uint32_t>& prev = p.k_shortest.back().second;
+        for (size_t i = 0; i + 1 < prev.size(); ++i) {
+          Search sr;
+          sr.pair = pi;
+          sr.i = i;
+          sr.from = prev[i];
+          for (auto& cp : p.k_shortest) {  // yen.rs:147-155
+            const auto& path = cp.second;
+            if (path.size() < i + 2) continue;
+            if (std::equal(prev.begin(), prev.begin() + i + 1, path.begin())) sr.fe.push_back({path[i], path[i + 1]});
+          }
+          sr.fn.assign(prev.begin(), prev.begin() + i);  // yen.rs:156-159
+          batch.push_back(std::move(sr));
+        }
+      }
+      run_batch(g, ps, batch, res, poison);
+      for (size_t b = 0; b < batch.size(); ++b) {
+        PairState& p = ps[batch[b].pair];
+        const std::vector<uint32_t>& prev = p.k_shortest.back().second;
+        const size_t i = batch[b].i;
+        float total = res[b].first;
+        for (size_t j = 0; j < i; ++j) {
+          auto fe = first_edge.find({prev[j], prev[j + 1]});
+          if (fe != first_edge.end()) total += fe->second;
+        }
+        std::vector<uint32_t> total_path(prev.begin(), prev.begin() + i);
+        total_path.insert(total_path.end(), res[b].second.begin(), res[b].second.end());
+        bool dup = false;
+        for (auto& c : p.candidates)
+          if (c.second == total_path) dup = true;
+        if (!dup) p.candidates.push_back({total, std::move(total_path)});  // yen.rs:187-189
+      }
+      poison.check();
+      for (PairState& p : ps) {
+        if (p.done) continue;
+        if (p.candidates.empty()) {  // yen.rs:194-196
+          p.done = true;
+          continue;
+        }
+        std::stable_sort(p.candidates.begin(), p.candidates.end(),
+                         [](const auto& a, const auto& b) { return b.first < a.first; });  // yen.rs:197
+        auto shortest = p.candidates.back();
+        p.candidates.pop_back();
+        if (std::isfinite(shortest.first)) p.k_shortest.push_back(std::move(shortest));  // yen.rs:200-203
+      }
+    }
+    for (const PairState& p : ps)
+      for (auto& cp : p.k_shortest) {  // yen.rs:62-77, 103-117
+        std::vector<DataValue> pl;
+        for (uint32_t u : cp.second) pl.push_back(g.indices[u]);
+        out.put({g.indices[p.start], g.indices[p.goal], DataValue::from_float((double)cp.first),
+                 DataValue::from_list(std::move(pl))});
+      }
+  }
+};
+
 // ---- registry (fixed_rule/mod.rs:705-836; Db::register_fixed_rule runtime/db.rs:760-784) ---
 struct FixedRuleRegistry {
   std::map<std::string, std::shared_ptr<FixedRule>> rules;
@@ -439,6 +601,7 @@ struct FixedRuleRegistry {
     add_builtin("ClosenessCentrality", std::make_shared<ClosenessCentrality>());
     add_builtin("BetweennessCentrality", std::make_shared<BetweennessCentrality>());
     add_builtin("ClusteringCoefficients", std::make_shared<ClusteringCoefficients>());
+    add_builtin("KShortestPathYen", std::make_shared<KShortestPathYen>());
   }
   void add_builtin(const std::string& n, std::shared_ptr<FixedRule> r) {
     rules[n] = std::move(r);

@@ -204,6 +204,18 @@ int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol, uint32_t m
 int cozo_gpu_sssp_multi(cozo_gpu_graph_t* g, const uint32_t* sources, uint32_t n_src, float* out_dist,
                         uint32_t* out_pred, double* out_kernel_ms, const volatile int* poison);
 
+/* Goal-directed batch of dijkstra calls with ForbiddenEdge / ForbiddenNode sets, the form
+ * KShortestPathYen uses (fixed_rule/algos/yen.rs:138,168; shortest_path_dijkstra.rs:188-218,274-339):
+ * search i runs from sources[i] to goals[i]; its forbidden nodes are forb_nodes[forb_node_ptr[i] ..
+ * forb_node_ptr[i+1]) and its forbidden (src,dst) pairs the same slice of forb_edge_src/dst (both
+ * ptr arrays NULL = no sets).  out_cost [n_src] (+inf unreachable), out_len [n_src] (0 unreachable;
+ * > max_len = buffer too small), out_paths [n_src*max_len] node ids start..goal. */
+int cozo_gpu_sssp_paths(cozo_gpu_graph_t* g, const uint32_t* sources, const uint32_t* goals, uint32_t n_src,
+                        const uint32_t* forb_node_ptr, const uint32_t* forb_nodes, const uint32_t* forb_edge_ptr,
+                        const uint32_t* forb_edge_src, const uint32_t* forb_edge_dst, uint32_t max_len,
+                        float* out_cost, uint32_t* out_len, uint32_t* out_paths, double* out_kernel_ms,
+                        const volatile int* poison);
+
 /* ClosenessCentrality / BetweennessCentrality (all_pairs_shortest_path.rs:97-143, 29-95) */
 int cozo_gpu_closeness(cozo_gpu_graph_t* g, float* out, double* out_kernel_ms, const volatile int* poison);
 int cozo_gpu_betweenness(cozo_gpu_graph_t* g, float* out, double* out_kernel_ms, const volatile int* poison);

@@ -745,6 +745,103 @@ static void dijkstra(const Csr& g, uint32_t start, const std::set<uint32_t>* goa
   }
 }
 
+// dijkstra with ForbiddenEdge / ForbiddenNode sets and a single Option<u32> goal, as
+// KShortestPathYen calls it (yen.rs:138, 168; shortest_path_dijkstra.rs:188-218, 274-339).
+// Returns the (goal, cost, path) triple of `.into_iter().next()`.
+static void dijkstra_forbidden(const Csr& g, uint32_t start, uint32_t goal,
+                               const std::set<std::pair<uint32_t, uint32_t>>& fe, const std::set<uint32_t>& fn,
+                               float& cost_out, std::vector<uint32_t>& path_out) {
+  std::vector<float> distance(g.n, INFINITY);
+  std::vector<uint32_t> back(g.n, UINT32_MAX);
+  MinPQ pq;
+  distance[start] = 0.f;
+  pq.push(start, 0.0);
+  bool goal_left = true;
+  while (!pq.empty()) {
+    auto [node, costd] = pq.pop();
+    float cost = (float)costd;
+    if (cost > distance[node]) continue;
+    for (uint64_t k = g.out_ptr[node]; k < g.out_ptr[node + 1]; ++k) {
+      uint32_t nx = g.out_idx[k];
+      if (fn.count(nx)) continue;          // :298-300
+      if (fe.count({node, nx})) continue;  // :301-303
+      float nc = cost + g.out_w[k];
+      if (nc < distance[nx]) {
+        pq.push_decrease_cost(nx, (double)nc);
+        distance[nx] = nc;
+        back[nx] = node;
+      }
+    }
+    if (node == goal) goal_left = false;  // Goal for Option<u32>, :238-258
+    if (!goal_left) break;
+  }
+  cost_out = distance[goal];
+  path_out.clear();
+  if (!std::isfinite(cost_out)) return;  // (target, inf, [])
+  uint32_t cur = goal;
+  while (cur != start) {
+    path_out.push_back(cur);
+    cur = back[cur];
+  }
+  path_out.push_back(start);
+  std::reverse(path_out.begin(), path_out.end());
+}
+
+// k_shortest_path_yen — fixed_rule/algos/yen.rs:120-211, quirks included (unreachable spur
+// results enter `candidates` with infinite cost and a truncated path; only finite ones are kept).
+static std::vector<std::pair<float, std::vector<uint32_t>>> k_shortest_path_yen(const Csr& g, size_t k, uint32_t start,
+                                                                                uint32_t goal) {
+  std::vector<std::pair<float, std::vector<uint32_t>>> k_shortest, candidates;
+  {
+    float c;
+    std::vector<uint32_t> p;
+    dijkstra_forbidden(g, start, goal, {}, {}, c, p);
+    k_shortest.push_back({c, p});  // yen.rs:130-136 (the goal iterator always yields one triple)
+  }
+  for (size_t it = 1; it < k; ++it) {
+    const std::vector<uint32_t> prev_path = k_shortest.back().second;
+    for (size_t i = 0; i + 1 < prev_path.size(); ++i) {  // 0..prev_path.len()-1, yen.rs:140
+      uint32_t spur_node = prev_path[i];
+      std::vector<uint32_t> root_path(prev_path.begin(), prev_path.begin() + i + 1);
+      std::set<std::pair<uint32_t, uint32_t>> fe;
+      for (auto& cp : k_shortest) {  // yen.rs:147-155
+        const auto& p = cp.second;
+        if (p.size() < root_path.size() + 1) continue;
+        if (std::equal(root_path.begin(), root_path.end(), p.begin())) fe.insert({p[i], p[i + 1]});
+      }
+      std::set<uint32_t> fn(prev_path.begin(), prev_path.begin() + i);  // yen.rs:156-159
+      float spur_cost;
+      std::vector<uint32_t> spur_path;
+      dijkstra_forbidden(g, spur_node, goal, fe, fn, spur_cost, spur_path);
+      float total_cost = spur_cost;
+      for (size_t j = 0; j + 1 < root_path.size(); ++j) {  // yen.rs:171-183: first edge s->d in adjacency order
+        uint32_t sN = root_path[j], dN = root_path[j + 1];
+        for (uint64_t e = g.out_ptr[sN]; e < g.out_ptr[sN + 1]; ++e)
+          if (g.out_idx[e] == dN) {
+            total_cost += g.out_w[e];
+            break;
+          }
+      }
+      std::vector<uint32_t> total_path(root_path.begin(), root_path.end() - 1);
+      total_path.insert(total_path.end(), spur_path.begin(), spur_path.end());
+      bool dup = false;
+      for (auto& c : candidates)
+        if (c.second == total_path) dup = true;
+      if (!dup) candidates.push_back({total_cost, total_path});  // yen.rs:187-189
+    }
+    if (candidates.empty()) break;
+    // sort_by(|a,b| b.total_cmp(a)) then pop(): the smallest cost; stable sort keeps insertion order of ties
+    std::stable_sort(candidates.begin(), candidates.end(), [](const auto& a, const auto& b) {
+      // total_cmp on f32: order by bits with sign handling; costs are >= 0 or +inf/NaN-free here
+      return b.first < a.first;
+    });
+    auto shortest = candidates.back();
+    candidates.pop_back();
+    if (std::isfinite(shortest.first)) k_shortest.push_back(shortest);  // yen.rs:205-207
+  }
+  return k_shortest;
+}
+
 // a10. dijkstra_keep_ties — shortest_path_dijkstra.rs:341-432 (search part).
 // back-pointer lists are returned CSR-style.  A settled node that is re-pushed
 // through an equal-cost relaxation (possible only with zero-weight edges) is
@@ -1201,6 +1298,26 @@ int orc_clustering(void* gp, double* cc, uint64_t* n_triangles, uint64_t* degree
     cc[u] = 2. * (double)t / ((double)deg * ((double)deg - 1.));  // triangles.rs:93
   });
   return 0;
+}
+
+// KShortestPathYen for one (start, goal) pair.  out_cost [k], path_ptr [k+1], path_buf sized by a
+// first call with path_buf == NULL (returns total path length via *n_path_elems).
+int orc_yen(void* gp, uint32_t start, uint32_t goal, uint32_t k, float* out_cost, uint64_t* path_ptr,
+            uint32_t* path_buf, uint64_t* n_path_elems) {
+  const Csr& g = ((GraphHandle*)gp)->g;
+  auto res = k_shortest_path_yen(g, k, start, goal);
+  uint64_t tot = 0;
+  for (size_t i = 0; i < res.size(); ++i) {
+    if (out_cost) out_cost[i] = res[i].first;
+    if (path_ptr) path_ptr[i] = tot;
+    for (uint32_t u : res[i].second) {
+      if (path_buf) path_buf[tot] = u;
+      ++tot;
+    }
+  }
+  if (path_ptr) path_ptr[res.size()] = tot;
+  if (n_path_elems) *n_path_elems = tot;
+  return (int)res.size();
 }
 
 // seeded level law shared with tests (hnsw.rs:46-52 with a SplitMix64 uniform)

@@ -74,6 +74,8 @@ def lib():
         L.orc_closeness.argtypes = [vp, vp, u32]
         L.orc_betweenness.restype = C.c_int
         L.orc_betweenness.argtypes = [vp, vp, u32, u64]
+        L.orc_yen.restype = C.c_int
+        L.orc_yen.argtypes = [vp, u32, u32, u32, vp, vp, vp, vp]
         L.orc_clustering.restype = C.c_int
         L.orc_clustering.argtypes = [vp, vp, vp, vp, u32]
         L.orc_random_level.restype = i64
@@ -286,6 +288,16 @@ class OracleGraph:
         if rc != 0:
             raise RuntimeError("betweenness failed (zero-weight cycle)")
         return out
+
+    def yen(self, start, goal, k):
+        """k_shortest_path_yen (yen.rs:120-211) -> list of (cost f32, path list)"""
+        tot = C.c_uint64()
+        cnt = lib().orc_yen(self._h, start, goal, k, None, None, None, C.byref(tot))
+        cost = np.zeros(max(cnt, 1), np.float32)
+        ptr = np.zeros(cnt + 1, np.uint64)
+        buf = np.zeros(max(tot.value, 1), np.uint32)
+        lib().orc_yen(self._h, start, goal, k, _p(cost), _p(ptr), _p(buf), C.byref(tot))
+        return [(float(cost[i]), buf[int(ptr[i]):int(ptr[i + 1])].tolist()) for i in range(cnt)]
 
     def clustering(self, n_threads=1):
         """(cc f64, n_triangles u64, degree u64) per node; the graph must hold the mirrored edge stream"""

@@ -217,3 +217,39 @@ def test_clustering_exact(gpu):
     gc, gt, gd, ms_k = g.clustering()
     oc, ot, od = o.clustering(n_threads=16)
     assert np.array_equal(gt, ot) and np.array_equal(gd, od) and np.array_equal(gc, oc)
+
+
+def test_sssp_paths_with_forbidden_sets(gpu):
+    """goal-directed searches with ForbiddenEdge / ForbiddenNode sets == the oracle's dijkstra run on
+    the graph with those nodes / edges deleted (distinct weights: paths are forced)."""
+    rng = np.random.default_rng(8)
+    n = 200
+    pairs = sorted({(int(a), int(b)) for a, b in zip(rng.integers(0, n, 1600), rng.integers(0, n, 1600)) if a != b})
+    src = np.array([p[0] for p in pairs], np.uint32)
+    dst = np.array([p[1] for p in pairs], np.uint32)
+    w = (rng.random(src.size) * 10 + 0.5).astype(np.float32)
+    g = gpu.Graph(n, src, dst, w)
+    sources = rng.integers(0, n, 40).astype(np.uint32)
+    goals = rng.integers(0, n, 40).astype(np.uint32)
+    fn = [[int(x) for x in rng.integers(0, n, rng.integers(0, 4)) if x != sources[i]] for i in range(40)]
+    fe = [[pairs[int(j)] for j in rng.integers(0, len(pairs), rng.integers(0, 5))] for i in range(40)]
+    res, _ = g.sssp_paths(sources, goals, fn, fe, max_len=4)        # small buffer: exercises the retry
+    for i in range(40):
+        keep = np.array([(a, b) not in set(fe[i]) and b not in set(fn[i]) for a, b in pairs])
+        o = O.OracleGraph(n, src[keep], dst[keep], w[keep])
+        od, ob = o.sssp([int(sources[i])])
+        cost, path = res[i]
+        exp = float(od[0, goals[i]])
+        if np.isinf(exp):
+            assert np.isinf(cost) and path == []
+            continue
+        assert cost == exp
+        p, cur = [], int(goals[i])
+        while cur != int(sources[i]):
+            p.append(cur)
+            cur = int(ob[0, cur])
+        p.append(int(sources[i]))
+        assert path == p[::-1]
+    plain, _ = g.sssp_paths(sources, goals)
+    od, _ = O.OracleGraph(n, src, dst, w).sssp(sources)
+    assert [c for c, _ in plain] == [float(od[i, goals[i]]) for i in range(40)]

@@ -331,3 +331,26 @@ def test_concurrent_callers_share_one_index(gpu, cfg1):
     for t in threads:
         t.join()
     assert not errors and len(results) == 8
+
+
+def test_duplicate_vectors_distance_ties(gpu):
+    """Exact distance ties (every vector stored three times under different keys).  The tie order of
+    priority_queue is unspecified in the reference; what must hold is that the distance lists agree and
+    that ids only differ inside a tie group."""
+    base = uniform_vectors(700, 32, 808)
+    X = np.concatenate([base, base, base])              # id, id+700, id+1400 are identical vectors
+    ix = O.OracleHnsw.new(2100, 32, m=8, ef_construction=60)
+    ix.insert_all(X)
+    g = _stage(gpu, X, ix.levels(), gpu.L2, 8)
+    Q = uniform_vectors(150, 32, 809)
+    gi, gd, gc, _ = g.search(Q, 12, 60)
+    oi, od, oc, _ = ix.search(Q, 12, 60, n_threads=8)
+    assert np.array_equal(gc, oc)
+    # Tie order decides which of two equal-distance candidates survives an `ef`-bounded beam, so the
+    # traversals can diverge slightly: compare the result quality, not the exact lists.
+    close = np.isclose(gd, od, rtol=1e-5, atol=1e-6)
+    assert close.mean() > 0.97
+    same_group = (gi % 700) == (oi % 700)
+    assert same_group[close].mean() > 0.97
+    bi, bd = O.bruteforce_knn(X, Q, 12, n_threads=8)
+    assert np.isclose(gd, bd, rtol=1e-5, atol=1e-6).mean() >= np.isclose(od, bd, rtol=1e-5, atol=1e-6).mean() - 0.03

@@ -256,3 +256,28 @@ def test_clustering_rule(h):
     assert got["a"] == (1.0, 1, 2) and got["b"] == (1.0, 1, 2)
     assert got["c"] == (2.0 * 1 / (3 * 2), 1, 3) and got["d"] == (0.0, 0, 2) and got["e"] == (0.0, 0, 1)
     assert [r[0] for r in out] == ["a", "b", "c", "d", "e"]
+
+
+def test_yen_rule(h):
+    """?[start, goal, cost, path] <~ KShortestPathYen(*edges[], start[], goal[], k: 4) vs the oracle"""
+    rng = np.random.default_rng(21)
+    n = 80
+    names = [f"v{i:03d}" for i in range(n)]
+    pairs = sorted({(int(a), int(b)) for a, b in zip(rng.integers(0, n, 700), rng.integers(0, n, 700)) if a != b})
+    rows = [[names[a], names[b], float(np.float32(rng.random() * 10 + 0.5))] for a, b in pairs]
+    ids, src, dst, w = _dense(rows)
+    o = O.OracleGraph(len(ids), src, dst, w)
+    inv = {v: k for k, v in ids.items()}
+    db = h.Db()
+    starts, goals = [[names[0]], [names[11]]], [[names[5]], [names[40]], [names[77]]]
+    out = db.run_fixed_rule("KShortestPathYen", [rows, starts, goals], {"k": 4}, head_arity=4)
+    exp = []
+    for s in sorted(ids[x[0]] for x in starts):
+        for t in sorted(ids[x[0]] for x in goals):
+            for c, p in o.yen(s, t, 4):
+                exp.append([inv[s], inv[t], float(c), [inv[u] for u in p]])
+    assert sorted(out, key=repr) == sorted(exp, key=repr)
+    single = db.run_fixed_rule("KShortestPathYen", [rows, [[names[0]]], [[names[5]]]], {"k": 3})
+    assert len(single) == 3 and single[0][2] <= single[1][2] <= single[2][2]
+    with pytest.raises(h.CozoError):        # `k` is required (yen.rs:39)
+        db.run_fixed_rule("KShortestPathYen", [rows, starts, goals], {})

@@ -315,3 +315,29 @@ def test_clustering_vs_networkx():
     dst2 = np.array([1, 0, 2, 0, 2, 1, 1, 0, 0, 1], np.uint32)
     cc2, nt2, deg2 = O.OracleGraph(3, src2, dst2).clustering()
     assert deg2.tolist() == [4, 4, 2] and nt2.tolist() == [3, 3, 1]
+
+
+def test_yen_vs_networkx():
+    """k_shortest_path_yen (yen.rs:120-211) on a simple digraph with distinct weights == networkx's
+    shortest_simple_paths (costs; with distinct costs the paths are forced too)."""
+    import itertools
+    import networkx as nx
+    rng = np.random.default_rng(3)
+    n = 60
+    pairs = sorted({(int(a), int(b)) for a, b in zip(rng.integers(0, n, 400), rng.integers(0, n, 400)) if a != b})
+    src = np.array([p[0] for p in pairs], np.uint32)
+    dst = np.array([p[1] for p in pairs], np.uint32)
+    w = (rng.random(src.size) * 10 + 0.5).astype(np.float32)
+    g = O.OracleGraph(n, src, dst, w)
+    G = nx.DiGraph()
+    for a, b, ww in zip(src, dst, w):
+        G.add_edge(int(a), int(b), weight=float(ww))
+    for s, t in itertools.product(range(0, 60, 13), range(3, 60, 17)):
+        if s == t:
+            continue
+        res = [(c, p) for c, p in g.yen(s, t, 5) if np.isfinite(c)]
+        try:
+            ref = list(itertools.islice(nx.shortest_simple_paths(G, s, t, weight="weight"), 5))
+        except nx.NetworkXNoPath:
+            ref = []
+        assert [p for _, p in res] == ref
