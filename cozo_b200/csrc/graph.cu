@@ -295,12 +295,16 @@ struct ForbiddenSets {
   const uint32_t *fn_ptr, *fn_nodes, *fe_ptr, *fe_src, *fe_dst;
 };
 
-template <bool FORB>
+// SMEM = the per-source state (8 B/node) and the two frontier flag arrays (1 B/node each) live in
+// shared memory (graphs up to ~22 k nodes); the final state is copied out for the read-out kernels.
+// A warp takes one frontier node at a time and its lanes stride the node's out-edges.
+template <bool FORB, bool SMEM>
 __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ out_ptr,
                                                    const uint32_t* __restrict__ out_idx,
                                                    const float* __restrict__ out_w, uint32_t n,
                                                    const uint32_t* __restrict__ sources, uint32_t n_src,
-                                                   unsigned long long* state, uint32_t* flags, ForbiddenSets fs) {
+                                                   unsigned long long* state, uint8_t* flags, ForbiddenSets fs) {
+  extern __shared__ __align__(16) uint8_t sssp_smem[];
   const uint32_t si = blockIdx.x;
   if (si >= n_src) return;
   uint32_t fnb = 0, fne = 0, feb = 0, fee = 0;
@@ -310,10 +314,13 @@ __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ 
     feb = fs.fe_ptr[si];
     fee = fs.fe_ptr[si + 1];
   }
-  unsigned long long* st = state + (size_t)si * n;
-  uint32_t* cur = flags + (size_t)si * 2 * n;
-  uint32_t* nxt = cur + n;
+  unsigned long long* gst = state + (size_t)si * n;
+  unsigned long long* st = SMEM ? reinterpret_cast<unsigned long long*>(sssp_smem) : gst;
+  uint8_t* cur = SMEM ? sssp_smem + (size_t)n * 8 : flags + (size_t)si * 2 * n;
+  uint8_t* nxt = cur + n;
   __shared__ int s_any;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
     st[v] = SSSP_INF;
     cur[v] = 0;
@@ -329,11 +336,14 @@ __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ 
   for (;;) {
     if (threadIdx.x == 0) s_any = 0;
     __syncthreads();
-    for (uint32_t u = threadIdx.x; u < n; u += blockDim.x) {
-      if (!cur[u]) continue;
-      cur[u] = 0;
+    bool any_local = false;
+    for (uint32_t u = warp; u < n; u += nwarps) {
+      if (!cur[u]) continue;  // warp-uniform
+      __syncwarp();
+      if (lane == 0) cur[u] = 0;
       const float du = __uint_as_float((uint32_t)(st[u] >> 32));
-      for (uint32_t k = out_ptr[u]; k < out_ptr[u + 1]; ++k) {
+      const uint32_t kb = out_ptr[u], ke = out_ptr[u + 1];
+      for (uint32_t k = kb + lane; k < ke; k += 32) {
         const uint32_t v = out_idx[k];
         if (FORB) {  // shortest_path_dijkstra.rs:298-303
           bool skip = false;
@@ -348,21 +358,40 @@ __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ 
           unsigned long long got = atomicCAS(&st[v], old, want);
           if (got == old) {
             nxt[v] = 1;
-            s_any = 1;
+            any_local = true;
             break;
           }
           old = got;
         }
       }
     }
+    if (any_local) s_any = 1;
     __syncthreads();
     const int any = s_any;
     __syncthreads();
     if (!any) break;
-    uint32_t* t = cur;
+    uint8_t* t = cur;
     cur = nxt;
     nxt = t;
   }
+  if (SMEM)
+    for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) gst[v] = st[v];
+}
+
+// launch helper: shared-memory variant when the state fits
+template <bool FORB>
+static cudaError_t launch_sssp(cozo_gpu_graph_t* g, const uint32_t* d_sources, uint32_t n_src,
+                               unsigned long long* state, uint8_t* flags, ForbiddenSets fs) {
+  const uint32_t n = g->n;
+  const size_t need = (size_t)n * 10;
+  if (need + 1024 <= device_info().smem_optin) {
+    cudaError_t e = cudaFuncSetAttribute(sssp_kernel<FORB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e != cudaSuccess) return e;
+    sssp_kernel<FORB, true><<<n_src, 256, need>>>(g->out_ptr, g->out_idx, g->out_w, n, d_sources, n_src, state, flags, fs);
+  } else {
+    sssp_kernel<FORB, false><<<n_src, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, d_sources, n_src, state, flags, fs);
+  }
+  return cudaGetLastError();
 }
 
 // goal-directed read-out (shortest_path_dijkstra.rs:318-336): walk the predecessors from the goal
@@ -868,8 +897,7 @@ static int sssp_chunks(cozo_gpu_graph_t* g, const uint32_t* sources_host, uint32
     }
     uint32_t c = std::min(chunk, n_src - s0);
     cudaMemcpy(dsrc.p, sources_host + s0, (size_t)c * 4, cudaMemcpyHostToDevice);
-    sssp_kernel<false><<<c, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc.as<uint32_t>(), c,
-                                   state.as<unsigned long long>(), flags.as<uint32_t>(), ForbiddenSets{});
+    launch_sssp<false>(g, dsrc.as<uint32_t>(), c, state.as<unsigned long long>(), flags.as<uint8_t>(), ForbiddenSets{});
     ret = per_chunk(s0, c, state.as<unsigned long long>(), dsrc.as<uint32_t>());
     cudaError_t ce = cudaDeviceSynchronize();
     if (!ret && ce != cudaSuccess) ret = set_error(COZO_GPU_ECUDA, "sssp failed: %s", cudaGetErrorString(ce));
@@ -1053,11 +1081,9 @@ extern "C" int cozo_gpu_sssp_paths(cozo_gpu_graph_t* g, const uint32_t* sources,
   COZO_CUDA(cudaEventCreate(&e1));
   cudaEventRecord(e0);
   if (forb)
-    sssp_kernel<true><<<n_src, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc.as<uint32_t>(), n_src,
-                                      state.as<unsigned long long>(), flags.as<uint32_t>(), fs);
+    launch_sssp<true>(g, dsrc.as<uint32_t>(), n_src, state.as<unsigned long long>(), flags.as<uint8_t>(), fs);
   else
-    sssp_kernel<false><<<n_src, 256>>>(g->out_ptr, g->out_idx, g->out_w, n, dsrc.as<uint32_t>(), n_src,
-                                       state.as<unsigned long long>(), flags.as<uint32_t>(), fs);
+    launch_sssp<false>(g, dsrc.as<uint32_t>(), n_src, state.as<unsigned long long>(), flags.as<uint8_t>(), fs);
   sssp_path_kernel<<<(n_src + 127) / 128, 128>>>(state.as<unsigned long long>(), n, dsrc.as<uint32_t>(),
                                                  dgoal.as<uint32_t>(), n_src, max_len, dc.as<float>(),
                                                  dl.as<uint32_t>(), dp.as<uint32_t>());
