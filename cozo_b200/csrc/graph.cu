@@ -26,6 +26,10 @@ struct cozo_gpu_graph {
   uint32_t n_blk = 0;
   uint32_t* med_rows = nullptr;   // rows with BLK_CAP < in-degree <= HUB_T: one warp each
   uint32_t n_med = 0;
+  // PageRank keeps its contribution vector in "hot-first" order: slot[v] = rank of v by out-degree
+  // (descending), in_idx_hot = slot[in_idx].  A source is gathered once per out-edge, so the few
+  // thousand hub sources that carry most of the edges share a few hundred cache lines (L1-resident).
+  uint32_t *slot = nullptr, *in_idx_hot = nullptr;
   // hub rows are cut into chunks of <= HUB_CHUNK in-edges, one CTA per chunk
   uint32_t *hub_chunk_ptr = nullptr, *chunk_beg = nullptr, *chunk_end = nullptr;
   uint32_t n_chunks = 0;
@@ -85,12 +89,29 @@ __global__ void find_hubs_kernel(const uint32_t* in_ptr, uint32_t n, uint32_t* h
 //   new[u] = base + d * sum_{v in in(u)} contrib[v];  err += |new[u]-old[u]| (f64)
 //   contrib'[u] = new[u] / out_degree(u)
 // 8 lanes per destination row; rows longer than HUB_T go to the hub kernel.
-__global__ void pr_init_kernel(const uint32_t* out_ptr, uint32_t n, float init, float* scores, float* contrib) {
+__global__ void pr_init_kernel(const uint32_t* out_ptr, const uint32_t* slot, uint32_t n, float init, float* scores,
+                               float* contrib) {
   uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= n) return;
   scores[u] = init;
   uint32_t od = out_ptr[u + 1] - out_ptr[u];
-  contrib[u] = od ? init / (float)od : 0.f;  // od==0: value is never read (no out edge leads anywhere)
+  contrib[slot[u]] = od ? init / (float)od : 0.f;  // od==0: value is never read (no out edge leads anywhere)
+}
+
+__global__ void pr_slot_kernel(const uint32_t* perm, uint32_t n, uint32_t* slot) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) slot[perm[r]] = r;
+}
+__global__ void pr_degkey_kernel(const uint32_t* out_ptr, uint32_t n, uint32_t* key, uint32_t* val) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < n) {
+    key[u] = 0xFFFFFFFFu - (out_ptr[u + 1] - out_ptr[u]);  // ascending sort => descending out-degree
+    val[u] = u;
+  }
+}
+__global__ void pr_relabel_kernel(const uint32_t* in_idx, const uint32_t* slot, uint64_t m, uint32_t* out) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < m) out[e] = slot[in_idx[e]];
 }
 
 __device__ __forceinline__ void block_add_err(double e, double* out) {
@@ -140,7 +161,8 @@ __device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t* a, uint64_t pol
 __global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict__ blk_start, uint32_t n_blk,
                                                       const uint32_t* __restrict__ in_ptr,
                                                       const uint32_t* __restrict__ in_idx,
-                                                      const uint32_t* __restrict__ out_ptr, float base, float damping,
+                                                      const uint32_t* __restrict__ out_ptr,
+                                                      const uint32_t* __restrict__ slot, float base, float damping,
                                                       const float* __restrict__ contrib_old,
                                                       float* __restrict__ contrib_new, float* __restrict__ scores,
                                                       double* err) {
@@ -178,7 +200,7 @@ __global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict
       e += (double)fabsf(nw - scores[r]);
       scores[r] = nw;
       const uint32_t od = out_ptr[r + 1] - out_ptr[r];
-      contrib_new[r] = od ? nw / (float)od : 0.f;
+      contrib_new[slot[r]] = od ? nw / (float)od : 0.f;
     }
     __syncwarp();
   }
@@ -189,7 +211,8 @@ __global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict
 __global__ void __launch_bounds__(256) pr_medium_kernel(const uint32_t* __restrict__ rows, uint32_t n_rows,
                                                         const uint32_t* __restrict__ in_ptr,
                                                         const uint32_t* __restrict__ in_idx,
-                                                        const uint32_t* __restrict__ out_ptr, float base,
+                                                        const uint32_t* __restrict__ out_ptr,
+                                                        const uint32_t* __restrict__ slot, float base,
                                                         float damping, const float* __restrict__ contrib_old,
                                                         float* __restrict__ contrib_new, float* __restrict__ scores,
                                                         double* err) {
@@ -218,7 +241,7 @@ __global__ void __launch_bounds__(256) pr_medium_kernel(const uint32_t* __restri
       e = (double)fabsf(nw - scores[r]);
       scores[r] = nw;
       const uint32_t od = out_ptr[r + 1] - out_ptr[r];
-      contrib_new[r] = od ? nw / (float)od : 0.f;
+      contrib_new[slot[r]] = od ? nw / (float)od : 0.f;
     }
   }
   block_add_err(e, err);
@@ -260,7 +283,8 @@ __global__ void __launch_bounds__(256) pr_hub_partial_kernel(const uint32_t* __r
 __global__ void __launch_bounds__(256) pr_hub_final_kernel(const uint32_t* __restrict__ hubs, uint32_t n_hubs,
                                                            const uint32_t* __restrict__ hub_chunk_ptr,
                                                            const float* __restrict__ partial,
-                                                           const uint32_t* __restrict__ out_ptr, float base,
+                                                           const uint32_t* __restrict__ out_ptr,
+                                                           const uint32_t* __restrict__ slot, float base,
                                                            float damping, float* __restrict__ contrib_new,
                                                            float* __restrict__ scores, double* err) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,7 +297,7 @@ __global__ void __launch_bounds__(256) pr_hub_final_kernel(const uint32_t* __res
     e = (double)fabsf(nw - scores[u]);
     scores[u] = nw;
     const uint32_t od = out_ptr[u + 1] - out_ptr[u];
-    contrib_new[u] = od ? nw / (float)od : 0.f;
+    contrib_new[slot[u]] = od ? nw / (float)od : 0.f;
   }
   block_add_err(e, err);
 }
@@ -623,7 +647,7 @@ extern "C" void cozo_gpu_graph_free(cozo_gpu_graph_t* g) {
   if (!g) return;
   void* ptrs[] = {g->out_ptr,  g->out_idx,       g->in_ptr,    g->in_idx,   g->out_w,
                   g->hubs,     g->blk_start,     g->hub_chunk_ptr, g->chunk_beg, g->chunk_end,
-                  g->med_rows};
+                  g->med_rows, g->slot,         g->in_idx_hot};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete g;
@@ -728,6 +752,26 @@ extern "C" int cozo_gpu_graph_stage(cozo_gpu_graph_t** out, uint32_t n, uint64_t
     G_CUDA(cudaDeviceSynchronize());
   }
   if (n) {
+    // hot-first slots for PageRank's contribution vector
+    DevBuf key, key2, val, perm, tmp2;
+    G_CUDA(cudaMalloc(&key.p, (size_t)n * 4));
+    G_CUDA(cudaMalloc(&key2.p, (size_t)n * 4));
+    G_CUDA(cudaMalloc(&val.p, (size_t)n * 4));
+    G_CUDA(cudaMalloc(&perm.p, (size_t)n * 4));
+    G_CUDA(cudaMalloc(&g->slot, (size_t)n * 4));
+    G_CUDA(cudaMalloc(&g->in_idx_hot, mm * 4));
+    pr_degkey_kernel<<<(n + 255) / 256, 256>>>(g->out_ptr, n, key.as<uint32_t>(), val.as<uint32_t>());
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, key.as<uint32_t>(), key2.as<uint32_t>(), val.as<uint32_t>(),
+                                    perm.as<uint32_t>(), (int)n);
+    G_CUDA(cudaMalloc(&tmp2.p, sb));
+    cub::DeviceRadixSort::SortPairs(tmp2.p, sb, key.as<uint32_t>(), key2.as<uint32_t>(), val.as<uint32_t>(),
+                                    perm.as<uint32_t>(), (int)n);
+    pr_slot_kernel<<<(n + 255) / 256, 256>>>(perm.as<uint32_t>(), n, g->slot);
+    if (m)
+      pr_relabel_kernel<<<(uint32_t)((m + 255) / 256), 256>>>(g->in_idx, g->slot, m, g->in_idx_hot);
+    G_CUDA(cudaGetLastError());
+    G_CUDA(cudaDeviceSynchronize());
     // row blocks for the pull kernel: consecutive rows, <= BLK_CAP in-edges and <= BLK_ROWS rows,
     // hub rows (in-degree > HUB_T) excluded and listed separately
     std::vector<uint32_t> hin(np1);
@@ -822,7 +866,7 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   const float init = 1.0f / (float)n;
   const float base = (1.0f - damping) / (float)n;
   COZO_CUDA(cudaEventRecord(e0));
-  pr_init_kernel<<<(n + 255) / 256, 256>>>(g->out_ptr, n, init, scores.as<float>(), c0.as<float>());
+  pr_init_kernel<<<(n + 255) / 256, 256>>>(g->out_ptr, g->slot, n, init, scores.as<float>(), c0.as<float>());
   float* cold = c0.as<float>();
   float* cnew = c1.as<float>();
   uint32_t iter = 0;
@@ -836,16 +880,16 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
     }
     cudaMemsetAsync(err.p, 0, 8);
     if (g->n_blk)
-      pr_iter_kernel<<<grid, 256>>>(g->blk_start, g->n_blk, g->in_ptr, g->in_idx, g->out_ptr, base, damping, cold,
+      pr_iter_kernel<<<grid, 256>>>(g->blk_start, g->n_blk, g->in_ptr, g->in_idx_hot, g->out_ptr, g->slot, base, damping, cold,
                                     cnew, scores.as<float>(), err.as<double>());
     if (g->n_med)
-      pr_medium_kernel<<<(g->n_med + 7) / 8, 256>>>(g->med_rows, g->n_med, g->in_ptr, g->in_idx, g->out_ptr, base,
+      pr_medium_kernel<<<(g->n_med + 7) / 8, 256>>>(g->med_rows, g->n_med, g->in_ptr, g->in_idx_hot, g->out_ptr, g->slot, base,
                                                      damping, cold, cnew, scores.as<float>(), err.as<double>());
     if (g->n_hubs) {
-      pr_hub_partial_kernel<<<g->n_chunks, 256>>>(g->chunk_beg, g->chunk_end, g->in_idx, cold, partial.as<float>());
+      pr_hub_partial_kernel<<<g->n_chunks, 256>>>(g->chunk_beg, g->chunk_end, g->in_idx_hot, cold, partial.as<float>());
       pr_hub_final_kernel<<<(g->n_hubs + 255) / 256, 256>>>(g->hubs, g->n_hubs, g->hub_chunk_ptr, partial.as<float>(),
-                                                            g->out_ptr, base, damping, cnew, scores.as<float>(),
-                                                            err.as<double>());
+                                                            g->out_ptr, g->slot, base, damping, cnew,
+                                                            scores.as<float>(), err.as<double>());
     }
     cudaError_t ce = cudaMemcpy(&herr, err.p, 8, cudaMemcpyDeviceToHost);
     if (ce != cudaSuccess) {
