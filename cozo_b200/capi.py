@@ -24,7 +24,7 @@ EXPORTS = [
     "cozo_gpu_init", "cozo_gpu_shutdown", "cozo_gpu_last_error", "cozo_gpu_device_count", "cozo_gpu_set_option",
     "cozo_gpu_get_option", "cozo_gpu_hnsw_stage", "cozo_gpu_hnsw_free", "cozo_gpu_hnsw_search",
     "cozo_gpu_hnsw_search_dev", "cozo_gpu_hnsw_search_scatter_dev", "cozo_gpu_hnsw_build", "cozo_gpu_hnsw_insert", "cozo_gpu_hnsw_remove", "cozo_gpu_hnsw_info", "cozo_gpu_hnsw_level_size",
-    "cozo_gpu_hnsw_export_level", "cozo_gpu_hnsw_vectors_dev", "cozo_gpu_topk_merge_dev", "cozo_gpu_graph_stage",
+    "cozo_gpu_hnsw_export_level", "cozo_gpu_hnsw_export_level_dist", "cozo_gpu_hnsw_export_live", "cozo_gpu_hnsw_vectors_dev", "cozo_gpu_topk_merge_dev", "cozo_gpu_graph_stage",
     "cozo_gpu_graph_free", "cozo_gpu_graph_export", "cozo_gpu_pagerank", "cozo_gpu_sssp_multi", "cozo_gpu_closeness",
     "cozo_gpu_betweenness", "cozo_gpu_clustering", "cozo_gpu_sssp_paths",
 ]
@@ -88,6 +88,8 @@ def load():
     L.cozo_gpu_hnsw_info.argtypes = [vp, vp, vp, vp, vp]
     L.cozo_gpu_hnsw_level_size.argtypes = [vp, u32, vp, vp]
     L.cozo_gpu_hnsw_export_level.argtypes = [vp, u32, vp, vp, vp]
+    L.cozo_gpu_hnsw_export_level_dist.argtypes = [vp, u32, vp]
+    L.cozo_gpu_hnsw_export_live.argtypes = [vp, vp]
     L.cozo_gpu_hnsw_vectors_dev.argtypes = [vp, vp]
     L.cozo_gpu_hnsw_vectors_dev.restype = vp
     L.cozo_gpu_topk_merge_dev.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp]
@@ -240,6 +242,21 @@ class HnswIndex:
             row_ptr.append(rp)
             col_idx.append(ci[:ne.value])
         return node_ids, row_ptr, col_idx, ep
+
+    def export_dists(self):
+        """stored edge distances per layer, aligned with export_levels()' col_idx"""
+        ni, rp, ci, ep = self.export_levels()
+        out = []
+        for lvl in range(len(ci)):
+            d = np.zeros(max(ci[lvl].size, 1), np.float32)
+            _check(load().cozo_gpu_hnsw_export_level_dist(self._h, lvl, _p(d)))
+            out.append(d[:ci[lvl].size])
+        return out
+
+    def export_live(self):
+        live = np.ones(self.info()[0], np.uint8)
+        _check(load().cozo_gpu_hnsw_export_live(self._h, _p(live)))
+        return live.astype(bool)
 
     def vectors_dev(self):
         stride = C.c_uint32()

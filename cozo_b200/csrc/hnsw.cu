@@ -681,44 +681,48 @@ extern "C" const float* cozo_gpu_hnsw_vectors_dev(cozo_gpu_hnsw_t* h, uint32_t* 
 
 // download one layer as CSR with rows sorted ascending (key order)
 static int fetch_level(cozo_gpu_hnsw_t* h, uint32_t level, std::vector<uint32_t>& node_ids,
-                       std::vector<uint64_t>& row_ptr, std::vector<uint32_t>& col_idx) {
+                       std::vector<uint64_t>& row_ptr, std::vector<uint32_t>& col_idx,
+                       std::vector<float>* dist = nullptr) {
   const HnswDev& g = h->dev;
   if (level >= h->n_levels) return set_error(COZO_GPU_EINVAL, "layer %u does not exist", level);
   node_ids.clear();
   row_ptr.assign(1, 0);
   col_idx.clear();
-  if (level == 0) {
-    std::vector<uint32_t> adj((size_t)g.n * g.s0);
-    if (g.n) COZO_CUDA(cudaMemcpy(adj.data(), g.adj0, adj.size() * 4, cudaMemcpyDeviceToHost));
-    for (uint32_t i = 0; i < g.n; ++i) {
-      node_ids.push_back(i);
-      size_t b = col_idx.size();
-      for (uint32_t j = 0; j < g.s0; ++j) {
-        uint32_t t = adj[(size_t)i * g.s0 + j];
-        if (t == NONE) break;
-        col_idx.push_back(t);
-      }
-      std::sort(col_idx.begin() + b, col_idx.end());
-      row_ptr.push_back(col_idx.size());
-    }
-  } else {
-    std::vector<uint32_t> adj((size_t)std::max<uint64_t>(h->up_rows, 1) * g.su);
-    std::vector<uint32_t> off(g.n);
-    COZO_CUDA(cudaMemcpy(adj.data(), g.adj_up, adj.size() * 4, cudaMemcpyDeviceToHost));
+  if (dist) dist->clear();
+  const uint32_t stride = level == 0 ? g.s0 : g.su;
+  const size_t rows = level == 0 ? (size_t)g.n : (size_t)std::max<uint64_t>(h->up_rows, 1);
+  std::vector<uint32_t> adj(rows * stride);
+  std::vector<float> adj_d;
+  std::vector<uint32_t> off;
+  if (!adj.empty())
+    COZO_CUDA(cudaMemcpy(adj.data(), level == 0 ? g.adj0 : g.adj_up, adj.size() * 4, cudaMemcpyDeviceToHost));
+  if (dist) {
+    const float* src = level == 0 ? h->d_adj0_dist : h->d_adj_up_dist;
+    if (!src) return set_error(COZO_GPU_EINVAL, "edge distances are not materialised");
+    adj_d.resize(adj.size());
+    if (!adj_d.empty()) COZO_CUDA(cudaMemcpy(adj_d.data(), src, adj_d.size() * 4, cudaMemcpyDeviceToHost));
+  }
+  if (level > 0) {
+    off.resize(g.n);
     if (g.n) COZO_CUDA(cudaMemcpy(off.data(), g.upper_off, (size_t)g.n * 4, cudaMemcpyDeviceToHost));
-    for (uint32_t i = 0; i < g.n; ++i) {
-      if (h->node_level[i] < level) continue;
-      node_ids.push_back(i);
-      size_t b = col_idx.size();
-      size_t row = (size_t)off[i] + level - 1;
-      for (uint32_t j = 0; j < g.su; ++j) {
-        uint32_t t = adj[row * g.su + j];
-        if (t == NONE) break;
-        col_idx.push_back(t);
-      }
-      std::sort(col_idx.begin() + b, col_idx.end());
-      row_ptr.push_back(col_idx.size());
+  }
+  std::vector<std::pair<uint32_t, float>> tmp;
+  for (uint32_t i = 0; i < g.n; ++i) {
+    if (h->node_level[i] < level) continue;
+    node_ids.push_back(i);
+    const size_t row = level == 0 ? (size_t)i : (size_t)off[i] + level - 1;
+    tmp.clear();
+    for (uint32_t j = 0; j < stride; ++j) {
+      uint32_t t = adj[row * stride + j];
+      if (t == NONE) break;
+      tmp.push_back({t, dist ? adj_d[row * stride + j] : 0.f});
     }
+    std::sort(tmp.begin(), tmp.end(), [](const auto& a, const auto& b) { return a.first < b.first; });  // key order
+    for (auto& e : tmp) {
+      col_idx.push_back(e.first);
+      if (dist) dist->push_back(e.second);
+    }
+    row_ptr.push_back(col_idx.size());
   }
   return 0;
 }
@@ -744,5 +748,27 @@ extern "C" int cozo_gpu_hnsw_export_level(cozo_gpu_hnsw_t* h, uint32_t level, ui
   if (node_ids) std::copy(ni.begin(), ni.end(), node_ids);
   if (row_ptr) std::copy(rp.begin(), rp.end(), row_ptr);
   if (col_idx) std::copy(ci.begin(), ci.end(), col_idx);
+  return 0;
+}
+
+// Stored `dist` of every edge of a layer (the index relation's value column, relation.rs:1064-1126),
+// aligned with the col_idx order of cozo_gpu_hnsw_export_level.
+extern "C" int cozo_gpu_hnsw_export_level_dist(cozo_gpu_hnsw_t* h, uint32_t level, float* dist) {
+  if (!h || !dist) return set_error(COZO_GPU_EINVAL, "null argument");
+  int rc = hnsw_ensure_build_state(h);
+  if (rc) return rc;
+  std::vector<uint32_t> ni, ci;
+  std::vector<uint64_t> rp;
+  std::vector<float> d;
+  rc = fetch_level(h, level, ni, rp, ci, &d);
+  if (rc) return rc;
+  std::copy(d.begin(), d.end(), dist);
+  return 0;
+}
+
+// 1 for every id that is still indexed (0 after cozo_gpu_hnsw_remove)
+extern "C" int cozo_gpu_hnsw_export_live(cozo_gpu_hnsw_t* h, uint8_t* live) {
+  if (!h || !live) return set_error(COZO_GPU_EINVAL, "null argument");
+  for (uint32_t i = 0; i < h->dev.n; ++i) live[i] = i < h->live.size() ? h->live[i] : 1;
   return 0;
 }

@@ -63,6 +63,53 @@ struct CompoundKeyLess {
   }
 };
 
+// SHA-256 (FIPS 180-4) of a vector's little-endian element bytes: Vector::get_hash (data/value.rs:333-348),
+// the `hash` column of the self-loop rows (hnsw.rs:168, 237-241).
+inline std::string sha256_le_f32(const std::vector<float>& v) {
+  static const uint32_t K[64] = {
+      0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98,
+      0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786,
+      0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8,
+      0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13,
+      0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819,
+      0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a,
+      0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7,
+      0xc67178f2};
+  std::string msg(reinterpret_cast<const char*>(v.data()), v.size() * 4);  // x86-64: already little endian
+  const uint64_t bitlen = (uint64_t)msg.size() * 8;
+  msg.push_back((char)0x80);
+  while (msg.size() % 64 != 56) msg.push_back(0);
+  for (int i = 7; i >= 0; --i) msg.push_back((char)((bitlen >> (8 * i)) & 0xff));
+  uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  auto rotr = [](uint32_t x, int n) { return (x >> n) | (x << (32 - n)); };
+  for (size_t off = 0; off < msg.size(); off += 64) {
+    uint32_t w[64];
+    for (int i = 0; i < 16; ++i)
+      w[i] = ((uint32_t)(uint8_t)msg[off + 4 * i] << 24) | ((uint32_t)(uint8_t)msg[off + 4 * i + 1] << 16) |
+             ((uint32_t)(uint8_t)msg[off + 4 * i + 2] << 8) | (uint32_t)(uint8_t)msg[off + 4 * i + 3];
+    for (int i = 16; i < 64; ++i) {
+      uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+      uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+      w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; ++i) {
+      uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+      uint32_t ch = (e & f) ^ (~e & g);
+      uint32_t t1 = hh + S1 + ch + K[i] + w[i];
+      uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+      uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+      uint32_t t2 = S0 + mj;
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+  }
+  std::string out(32, 0);
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j < 4; ++j) out[4 * i + j] = (char)((h[i] >> (24 - 8 * j)) & 0xff);
+  return out;
+}
+
 // The device-resident copy of one index: a cache of the index relation.
 struct StagedHnswIndex {
   cozo_gpu_hnsw_t* h = nullptr;
@@ -214,6 +261,138 @@ struct StagedHnswIndex {
       h = nullptr;
     }
     gpu_check(cozo_gpu_hnsw_stage(&h, &d));
+  }
+
+  // create_hnsw_index (runtime/relation.rs:1010-1201): index every vector of the base relation in key
+  // order (single vectors and list-of-vectors columns, hnsw.rs:694-706), on the device.
+  void build(const RelationHandle& base, const HnswIndexManifest& mf, uint64_t level_seed = 0x5EED0003ull) {
+    manifest = mf;
+    if (mf.dtype_f64)
+      throw CozoError("gpu::unsupported", "F64 vector indexes are outside the device envelope (f32 only)");
+    keys.clear();
+    std::vector<float> vectors;
+    for (auto& kv : base.rows) {
+      for (size_t fld : mf.vec_fields) {
+        const DataValue& val = kv.second.at(fld);
+        auto push = [&](const DataValue& v, int32_t sub) {
+          if (v.kind != DataValue::Vec) return;
+          if (v.v->size() != mf.vec_dim) throw CozoError("", "vector dimension mismatch for the index");
+          keys.emplace_back(kv.first, fld, sub);
+          vectors.insert(vectors.end(), v.v->begin(), v.v->end());
+        };
+        if (val.kind == DataValue::Vec) push(val, -1);
+        else if (val.kind == DataValue::List)
+          for (size_t i = 0; i < val.list.size(); ++i) push(val.list[i], (int32_t)i);
+      }
+    }
+    // keys are generated row by row, field by field: sort into compound-key order (dense id = key order)
+    std::vector<size_t> order(keys.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return CompoundKeyLess()(keys[a], keys[b]); });
+    std::vector<CompoundKey> k2(keys.size());
+    std::vector<float> v2(vectors.size());
+    for (size_t r = 0; r < order.size(); ++r) {
+      k2[r] = keys[order[r]];
+      std::copy(vectors.begin() + order[r] * mf.vec_dim, vectors.begin() + (order[r] + 1) * mf.vec_dim,
+                v2.begin() + r * mf.vec_dim);
+    }
+    keys.swap(k2);
+    if (h) {
+      cozo_gpu_hnsw_free(h);
+      h = nullptr;
+    }
+    if (keys.empty()) {  // nothing to index yet: an empty staged index (canary only)
+      CozoGpuHnswLevel l0{};
+      uint64_t zero = 0;
+      l0.row_ptr = &zero;
+      CozoGpuHnswStageDesc d{};
+      d.dim = (uint32_t)mf.vec_dim;
+      d.metric = (int32_t)mf.distance;
+      d.n_levels = 1;
+      d.levels = &l0;
+      d.entry_point = COZO_GPU_NONE;
+      d.m_max0 = (uint32_t)mf.m_max0;
+      d.m_max = (uint32_t)mf.m_max;
+      float dummy = 0;
+      d.vectors = &dummy;
+      gpu_check(cozo_gpu_hnsw_stage(&h, &d));
+      return;
+    }
+    CozoGpuHnswBuildDesc d{};
+    d.n_vectors = (uint32_t)keys.size();
+    d.dim = (uint32_t)mf.vec_dim;
+    d.metric = (int32_t)mf.distance;
+    d.vectors = v2.data();
+    d.m_neighbours = (uint32_t)mf.m_neighbours;
+    d.ef_construction = (uint32_t)mf.ef_construction;
+    d.extend_candidates = mf.extend_candidates;
+    d.keep_pruned_connections = mf.keep_pruned_connections;
+    d.level_seed = level_seed;
+    gpu_check(cozo_gpu_hnsw_build(&h, &d));
+  }
+
+  // The rows of `rel:idx` (runtime/relation.rs:1064-1126) that describe the device
+  // copy: the canary, one self-loop row per (node, layer) carrying the degree and the vector's SHA-256,
+  // one row per directed edge carrying the stored distance.  Feeding them back to stage() reproduces
+  // the same index.
+  std::vector<Tuple> to_index_rows(const RelationHandle& base) const {
+    const size_t K = base.keys.size();
+    uint32_t n = 0, dim = 0, n_levels = 0, entry = COZO_GPU_NONE;
+    gpu_check(cozo_gpu_hnsw_info(h, &n, &dim, &n_levels, &entry));
+    std::vector<uint8_t> live(std::max<uint32_t>(n, 1), 1);
+    if (n) gpu_check(cozo_gpu_hnsw_export_live(h, live.data()));
+    auto key_part = [&](Tuple& t, uint32_t id) {
+      const CompoundKey& ck = keys[id];
+      t.insert(t.end(), std::get<0>(ck).begin(), std::get<0>(ck).end());
+      t.push_back(DataValue::from_int((int64_t)std::get<1>(ck)));
+      t.push_back(DataValue::from_int((int64_t)std::get<2>(ck)));
+    };
+    std::vector<Tuple> rows;
+    if (entry == COZO_GPU_NONE) return rows;  // the last vector was removed: the canary goes too (hnsw.rs:861-864)
+    {  // canary (hnsw.rs:642-669): (1, Null x (2K+4)) => (top layer, key bytes of the entry's self loop, false)
+      Tuple t{DataValue::from_int(1)};
+      for (size_t i = 0; i < 2 * K + 4; ++i) t.push_back(DataValue::null());
+      t.push_back(DataValue::from_int(-(int64_t)(n_levels - 1)));
+      t.push_back(DataValue::from_bytes("entry:" + std::to_string(entry)));
+      t.push_back(DataValue::from_bool(false));
+      rows.push_back(std::move(t));
+    }
+    for (uint32_t L = 0; L < n_levels; ++L) {
+      uint32_t nn = 0;
+      uint64_t ne = 0;
+      gpu_check(cozo_gpu_hnsw_level_size(h, L, &nn, &ne));
+      std::vector<uint32_t> ni(std::max<uint32_t>(nn, 1)), ci(std::max<uint64_t>(ne, 1));
+      std::vector<uint64_t> rp((size_t)nn + 1);
+      std::vector<float> ds(std::max<uint64_t>(ne, 1));
+      gpu_check(cozo_gpu_hnsw_export_level(h, L, ni.data(), rp.data(), ci.data()));
+      gpu_check(cozo_gpu_hnsw_export_level_dist(h, L, ds.data()));
+      for (uint32_t r = 0; r < nn; ++r) {
+        const uint32_t id = ni[r];
+        if (!live[id]) continue;
+        const CompoundKey& ck = keys[id];
+        const Tuple* brow = base.get(std::get<0>(ck));
+        const DataValue* field = brow ? &(*brow)[std::get<1>(ck)] : nullptr;
+        if (field && std::get<2>(ck) >= 0) field = &field->list[(size_t)std::get<2>(ck)];
+        Tuple self{DataValue::from_int(-(int64_t)L)};
+        key_part(self, id);
+        key_part(self, id);
+        self.push_back(DataValue::from_float((double)(rp[r + 1] - rp[r])));  // degree (hnsw.rs:269-277)
+        self.push_back(DataValue::from_bytes(field && field->v ? sha256_le_f32(*field->v) : std::string()));
+        self.push_back(DataValue::from_bool(false));
+        rows.push_back(std::move(self));
+        for (uint64_t e = rp[r]; e < rp[r + 1]; ++e) {
+          Tuple t{DataValue::from_int(-(int64_t)L)};
+          key_part(t, id);
+          key_part(t, ci[e]);
+          t.push_back(DataValue::from_float((double)ds[e]));  // hnsw.rs:281-298
+          t.push_back(DataValue::null());
+          t.push_back(DataValue::from_bool(false));
+          rows.push_back(std::move(t));
+        }
+      }
+    }
+    std::sort(rows.begin(), rows.end(), TupleLess());
+    return rows;
   }
 };
 

@@ -130,6 +130,23 @@ struct PyHnswIndex {
     m.derive();
     ix.stage(base.rel, to_rows(idx_rows), m);
   }
+  static HnswIndexManifest manifest_of(py::dict mf) {
+    HnswIndexManifest m;
+    m.vec_dim = mf["dim"].cast<size_t>();
+    m.m_neighbours = mf["m"].cast<size_t>();
+    m.ef_construction = mf["ef_construction"].cast<size_t>();
+    m.vec_fields = mf["fields"].cast<std::vector<size_t>>();
+    std::string dist = mf.contains("distance") ? mf["distance"].cast<std::string>() : "L2";
+    if (dist == "L2") m.distance = HnswDistance::L2;
+    else if (dist == "Cosine") m.distance = HnswDistance::Cosine;
+    else if (dist == "IP") m.distance = HnswDistance::InnerProduct;
+    else throw CozoError("", "Invalid distance: " + dist);
+    if (mf.contains("keep_pruned_connections")) m.keep_pruned_connections = mf["keep_pruned_connections"].cast<bool>();
+    m.derive();
+    return m;
+  }
+  void build(const PyRelation& base, py::dict mf) { ix.build(base.rel, manifest_of(mf)); }
+  py::list to_index_rows(const PyRelation& base) const { return from_rows(ix.to_index_rows(base.rel)); }
   py::dict info() const {
     py::dict d;
     d["n_vectors"] = ix.keys.size();
@@ -202,6 +219,8 @@ PYBIND11_MODULE(_cozo_host, m) {
   py::class_<PyHnswIndex, std::shared_ptr<PyHnswIndex>>(m, "HnswIndex")
       .def(py::init<>())
       .def("stage", &PyHnswIndex::stage)
+      .def("build", &PyHnswIndex::build)
+      .def("to_index_rows", &PyHnswIndex::to_index_rows)
       .def("info", &PyHnswIndex::info);
   py::class_<PyHnswSearchRA>(m, "HnswSearchRA")
       .def(py::init<std::shared_ptr<PyRelation>, std::shared_ptr<PyHnswIndex>, size_t, size_t, py::object, bool, bool,
@@ -212,4 +231,7 @@ PYBIND11_MODULE(_cozo_host, m) {
       .def("iter", &PyHnswSearchRA::iter)
       .def("stats", &PyHnswSearchRA::stats);
   m.def("cmp", [](py::handle a, py::handle b) { return cmp(to_dv(a), to_dv(b)); });
+  m.def("sha256_le_f32", [](py::array_t<float, py::array::c_style | py::array::forcecast> a) {
+    return py::bytes(sha256_le_f32(std::vector<float>(a.data(), a.data() + a.size())));
+  });
 }

