@@ -156,8 +156,10 @@ static KernelFn pick_nv(uint32_t need, int metric, bool bulk) {
   return nullptr;
 }
 
-// 4 CTAs x 4 warps per SM (<= 128 registers).  A 7-CTA / 72-register build was measured
-// slower (17.5 ms vs 12.1 ms per 4096-query batch at 1M x 768: spills + 2-deep rings).
+// 4 CTAs x 4 warps per SM (<= 128 registers).  Builds capped for more resident warps were measured
+// slower per 4096-query batch at 1M x 768 (profiles/r01_sweep3_minblocks.txt): 5 CTAs / 96 regs 12.3 ms,
+// 6 CTAs / 80 regs 14.9 ms, 7 CTAs / 72 regs 17.5 ms, vs 12.1-12.2 ms here: the batch is bandwidth-bound,
+// and the tighter register budgets cost instructions.
 static KernelFn pick_kernel(uint32_t ld, int metric, bool bulk) {
   uint32_t need = (ld / 4 + 31) / 32;
   return pick_nv<4>(need, metric, bulk);
