@@ -1,0 +1,74 @@
+"""BASELINE-size checks through size-independent properties (the oracle cannot run these sizes in
+seconds): HNSW at configs[1] (1M x 768, ef=200, k=10, batch 4096) and PageRank at configs[3]
+(RMAT scale 24, 268M edges)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big(gpu):
+    import torch
+    from bench import gen_vectors
+    n, dim = 1_000_000, 768
+    X = gen_vectors(n, dim, 0x5EED0001)
+    g = gpu.HnswIndex.build(X, m=16, ef_construction=200, level_seed=0x5EED0003)
+    Q = gen_vectors(4096, dim, 0x5EED0002)
+    return X, g, Q, torch
+
+
+def test_hnsw_1m_properties(gpu, big):
+    X, g, Q, torch = big
+    ids, dist, cnt, st = g.search(Q, 10, 200)
+    assert np.all(cnt == 10) and np.all(ids < 1_000_000)
+    assert np.all(np.diff(dist, axis=1) >= 0)                                  # nearest first (hnsw.rs:1005)
+    assert all(len(set(r)) == 10 for r in ids[:512])                           # a row is never reported twice
+    # every reported distance is the true squared-L2 distance (recomputed in f64)
+    Xd = torch.from_numpy(X[ids[:1024].astype(np.int64).ravel()]).cuda().double().view(1024, 10, -1)
+    Qd = torch.from_numpy(Q[:1024]).cuda().double()[:, None, :]
+    true = ((Xd - Qd) ** 2).sum(-1).cpu().numpy()
+    assert np.allclose(dist[:1024], true, rtol=2e-6)
+    # k only truncates the ef-bounded beam (hnsw.rs:943-947): k=10 is the prefix of k=100
+    ids100, dist100, cnt100, _ = g.search(Q[:512], 100, 200)
+    assert np.array_equal(ids100[:, :10], ids[:512]) and np.all(cnt100 == 100)
+    # radius drops exactly the tail beyond it (hnsw.rs:952-956)
+    r = float(np.median(dist[:512, 4]))
+    idr, dr, cr, _ = g.search(Q[:512], 10, 200, radius=r)
+    assert np.array_equal(cr, (dist[:512] <= r).sum(1)) and np.all(dr[np.isfinite(dr)] <= r)
+    # an indexed vector that finds itself does so at distance exactly 0.  (On i.i.d. uniform 768-d data
+    # distances concentrate and HNSW with m=16 / ef=200 finds only ~16 % of the stored vectors — a
+    # property of this synthetic workload, which the reference algorithm shares; parity is vs the oracle.)
+    own, d0, _, _ = g.search(X[:2048], 1, 200)
+    hit = own[:, 0] == np.arange(2048)
+    assert hit.mean() > 0.05 and np.all(d0[hit, 0] == 0) and np.all(d0[~hit, 0] > 0)
+    # a larger beam never lowers the quality of the answer
+    ids64, dist64, _, _ = g.search(Q[:512], 10, 64)
+    assert dist[:512].sum() <= dist64.sum() and (dist[:512, 9] <= dist64[:, 9] + 1e-6).mean() > 0.99
+    # the traversal counters that feed the roofline are plausible and stable
+    assert 5000 < st.dist_evals / 4096 < 8000 and st.nodes_expanded >= 200 * 4096
+    again = g.search(Q, 10, 200)
+    assert np.array_equal(again[0], ids) and again[3].dist_evals == st.dist_evals
+
+
+def test_pagerank_rmat24_first_iteration(gpu):
+    """one pull iteration from the uniform start has a closed form: base + d*init*sum_{v in in(u)} 1/outdeg(v)"""
+    import torch
+    from tools.bench_pagerank import rmat_torch
+    n, src, dst = rmat_torch(24, 16, 0x5EED0004)
+    assert n == 1 << 24 and src.size == 1 << 28
+    g = gpu.Graph(n, src, dst)
+    scores, it, err, ms = g.pagerank(0.85, 0.0, 1)
+    assert it == 1
+    s = torch.from_numpy(src.view(np.int32)).cuda().long()
+    d = torch.from_numpy(dst.view(np.int32)).cuda().long()
+    outdeg = torch.bincount(s, minlength=n).double()
+    contrib = (1.0 / n) / outdeg
+    exp = torch.full((n,), 0.15 / n, dtype=torch.float64, device="cuda")
+    exp.index_add_(0, d, 0.85 * contrib[s])
+    got = torch.from_numpy(scores).cuda().double()
+    rel = ((got - exp).abs() / exp).max().item()
+    assert rel <= 5e-6, rel
+    # default options of the rule (theta .85, epsilon 1e-4, iterations 10): the iteration cap binds
+    sc, it, err, _ = g.pagerank()
+    assert it == 10 and np.all(np.isfinite(sc)) and sc.min() >= np.float32(0.15 / n) * (1 - 1e-6)
