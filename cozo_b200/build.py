@@ -78,7 +78,7 @@ def build_host(force: bool = False) -> str:
     host = os.path.join(HERE, "host")
     ext = sysconfig.get_config_var("EXT_SUFFIX")
     out = os.path.join(host, "_cozo_host" + ext)
-    deps = [os.path.join(host, f) for f in ("pymod.cpp", "data_value.hpp", "fixed_rule.hpp", "hnsw.hpp")]
+    deps = [os.path.join(host, f) for f in ("pymod.cpp", "data_value.hpp", "fixed_rule.hpp", "hnsw.hpp", "memcmp.hpp")]
     deps.append(os.path.join(CSRC, "..", "..", "include", "cozo_gpu.h"))
     if force or _stale(out, deps) or _stale(out, [OUT]):
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",

@@ -6,6 +6,7 @@
 #include <pybind11/stl.h>
 
 #include "hnsw.hpp"
+#include "memcmp.hpp"
 
 namespace py = pybind11;
 using namespace cozo_host;
@@ -231,6 +232,30 @@ PYBIND11_MODULE(_cozo_host, m) {
       .def("iter", &PyHnswSearchRA::iter)
       .def("stats", &PyHnswSearchRA::stats);
   m.def("cmp", [](py::handle a, py::handle b) { return cmp(to_dv(a), to_dv(b)); });
+  // memcmp key codec (data/memcmp.rs, data/tuple.rs)
+  m.def("memcmp_encode_value", [](py::handle v) {
+    std::string o;
+    memcmp_codec::encode_datavalue(o, to_dv(v));
+    return py::bytes(o);
+  });
+  m.def("memcmp_decode_value", [](py::bytes b) {
+    std::string s = b;
+    DataValue v;
+    size_t used = memcmp_codec::decode_datavalue(reinterpret_cast<const uint8_t*>(s.data()), s.size(), v);
+    return py::make_tuple(from_dv(v), used);
+  });
+  m.def("memcmp_encode_bytes", [](py::bytes b) {
+    std::string o;
+    memcmp_codec::encode_bytes(o, b);
+    return py::bytes(o);
+  });
+  m.def("memcmp_decode_bytes", [](py::bytes b) {
+    std::string s = b, key;
+    size_t used = memcmp_codec::decode_bytes(reinterpret_cast<const uint8_t*>(s.data()), s.size(), key);
+    return py::make_tuple(py::bytes(key), used);
+  });
+  m.def("memcmp_encode_key", [](py::handle tuple, uint64_t rel) { return py::bytes(memcmp_codec::encode_as_key(to_tuple(tuple), rel)); });
+  m.def("memcmp_decode_key", [](py::bytes b) { return from_tuple(memcmp_codec::decode_tuple_from_key(b)); });
   m.def("sha256_le_f32", [](py::array_t<float, py::array::c_style | py::array::forcecast> a) {
     return py::bytes(sha256_le_f32(std::vector<float>(a.data(), a.data() + a.size())));
   });
