@@ -132,6 +132,127 @@ __global__ void __launch_bounds__(128, MINB) hnsw_search_kernel(HnswDev g, Searc
 
 using KernelFn = void (*)(HnswDev, SearchParams);
 
+// Cooperative form: one CTA (4 warps) per query; see coop_search_level.  Shared memory per CTA:
+// [fd ef][fi ef][pend 32][pdist 32][ctrl 8] then per warp [bars ns][ring ns rows].
+template <int NV, int METRIC>
+__global__ void __launch_bounds__(128, 4) hnsw_search_coop_kernel(HnswDev g, SearchParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  WarpCtx w;
+  w.fd = reinterpret_cast<float*>(smem);
+  w.fi = reinterpret_cast<uint32_t*>(smem + p.off_fi);
+  w.pend = nullptr;
+  CoopShared cs;
+  cs.pend = reinterpret_cast<uint32_t*>(smem + p.off_pend);
+  cs.pdist = reinterpret_cast<float*>(smem + p.off_pend + 128);
+  cs.ctrl = reinterpret_cast<uint32_t*>(smem + p.off_pend + 256);
+  uint8_t* wbase = smem + p.off_bars + (size_t)warp * p.warp_smem;  // off_bars = start of the per-warp region
+  w.bars = reinterpret_cast<uint64_t*>(wbase);
+  w.ring = reinterpret_cast<float*>(wbase + p.off_ring);            // off_ring = ring offset inside the region
+  const size_t slot = blockIdx.x;
+  w.vis = p.vis + slot * p.nwords;
+  w.nwords = p.nwords;
+  w.vlog = p.vlog + slot * p.logcap;
+  w.logcap = p.logcap;
+  w.ns = p.ns;
+  w.nlog = 0;
+  w.head = 0;
+  w.phase = 0;
+  w.len = 0;
+  w.cursor = 0;
+  if (lane == 0) {
+    for (uint32_t s = 0; s < p.ns; ++s) mbar_init(&w.bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int nvec4 = g.ld >> 2;
+  for (;;) {
+    if (threadIdx.x == 0) cs.ctrl[1] = atomicAdd(p.counter, 1u);
+    __syncthreads();
+    const uint32_t qi = cs.ctrl[1];
+    __syncthreads();
+    if (qi >= p.B) break;
+    float4 q[NV];
+    float qnorm;
+    load_query<NV>(p.queries + (size_t)qi * g.dim, g.dim, lane, q, qnorm);
+    w.len = 0;
+    w.cursor = 0;
+    w.dist_evals = w.nodes_expanded = w.nbr_reads = 0;
+    uint32_t found = 0;
+    if (g.entry != NONE) {
+      if (warp == 0) {
+        float d = dist_ldg1<NV, METRIC>(q, reinterpret_cast<const float4*>(g.vec + (size_t)g.entry * g.ld), lane,
+                                        nvec4, qnorm);
+        w.dist_evals = 1;
+        if (lane == 0) {
+          w.fd[0] = d;
+          w.fi[0] = g.entry;
+        }
+        w.len = 1;
+      }
+      __syncthreads();
+      for (uint32_t lvl = g.top_level; lvl >= 1; --lvl)
+        coop_search_level<NV, METRIC>(g, w, cs, q, qnorm, 1, lvl, lane, warp);
+      coop_search_level<NV, METRIC>(g, w, cs, q, qnorm, p.ef, 0, lane, warp);
+      if (warp == 0) {
+        found = w.len < p.k ? w.len : p.k;
+        if (p.has_radius) {
+          uint32_t c = 0;
+          for (uint32_t base_i = 0; base_i < found; base_i += 32) {
+            uint32_t i = base_i + lane;
+            bool in = i < found && !((double)w.fd[i] > p.radius);
+            c += __popc(__ballot_sync(0xffffffffu, in));
+          }
+          found = c;
+        }
+      }
+    }
+    if (warp == 0) {
+      for (uint32_t i = lane; i < p.k; i += 32) {
+        const bool in = i < found;
+        const uint32_t oid = in ? (w.fi[i] & IDMASK) : NONE;
+        const float od = in ? w.fd[i] : INFINITY;
+        if (p.out_ids) {
+          p.out_ids[(size_t)qi * p.k + i] = oid;
+          p.out_dist[(size_t)qi * p.k + i] = od;
+        }
+        const size_t at = ((size_t)p.slot * p.B + qi) * p.k + i;
+        for (uint32_t d = 0; d < p.n_dest; ++d) {
+          p.dest_ids[d][at] = oid;
+          p.dest_dist[d][at] = od;
+        }
+      }
+      if (lane == 0) {
+        if (p.out_count) p.out_count[qi] = found;
+        if (p.qstats) reinterpret_cast<uint4*>(p.qstats)[qi] = make_uint4(w.dist_evals, w.nodes_expanded, w.nbr_reads, 0);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int NV>
+static KernelFn pick_coop_metric(int metric) {
+  switch (metric) {
+    case COZO_GPU_L2: return hnsw_search_coop_kernel<NV, COZO_GPU_L2>;
+    case COZO_GPU_COSINE: return hnsw_search_coop_kernel<NV, COZO_GPU_COSINE>;
+    default: return hnsw_search_coop_kernel<NV, COZO_GPU_IP>;
+  }
+}
+static KernelFn pick_coop_kernel(uint32_t ld, int metric) {
+  uint32_t need = (ld / 4 + 31) / 32;
+  if (need <= 1) return pick_coop_metric<1>(metric);
+  if (need <= 2) return pick_coop_metric<2>(metric);
+  if (need <= 4) return pick_coop_metric<4>(metric);
+  if (need <= 6) return pick_coop_metric<6>(metric);
+  if (need <= 8) return pick_coop_metric<8>(metric);
+  if (need <= 16) return pick_coop_metric<16>(metric);
+  return nullptr;
+}
+
+
+
 template <int NV, int MINB>
 static KernelFn pick_metric(int metric, bool bulk) {
   switch (metric) {
@@ -276,41 +397,73 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
   const DeviceInfo& di = device_info();
   const HnswDev& g = h->dev;
   if (B == 0) return 0;
-  const bool bulk = get_option("hnsw.mode", 1) != 0;
-  uint32_t wpc = (uint32_t)get_option("hnsw.warps_per_cta", 4);
-  if (wpc < 1) wpc = 1;
-  if (wpc > 4) wpc = 4;  // __launch_bounds__(128, ..)
+  // mode 0: plain ld.global rows, 1: warp per query + TMA ring, 2: CTA per query (cooperative),
+  // -1 (default): cooperative when the batch cannot give every resident warp slot a query
+  int64_t mode = get_option("hnsw.mode", -1);
   uint32_t ns = (uint32_t)get_option("hnsw.stages", 4);
   if (ns < 1) ns = 1;
   if (ns > 32) ns = 32;
-  if (!bulk) ns = 0;
-  KernelFn fn = pick_kernel(g.ld, g.metric, bulk);
-  if (!fn) return set_error(COZO_GPU_EUNSUP, "vec_dim %u exceeds the supported maximum 2048", g.dim);
-
+  // measured crossover at 1M x 768 (profiles/r01_batch_sweep_1Mx768.txt): the cooperative kernel wins up to
+  // about 1.5 waves of CTAs (592 resident), the warp-per-query kernel beyond
+  const uint32_t coop_below = (uint32_t)get_option("hnsw.coop_below", (int64_t)di.sm_count * 6);
+  if (mode < 0) mode = B < coop_below ? 2 : 1;
   SearchParams p{};
   uint32_t efcap = round_up(ef, 32);
-  p.off_fi = efcap * 4;
-  p.off_pend = p.off_fi + efcap * 4;
-  p.off_bars = p.off_pend + 32 * 4;
-  p.off_ring = round_up(p.off_bars + ns * 8, 128);
-  p.warp_smem = round_up(p.off_ring + ns * g.ld * 4, 128);
-  size_t smem = (size_t)p.warp_smem * wpc;
-  while (smem > di.smem_optin && wpc > 1) {
-    wpc >>= 1;
+  KernelFn fn = nullptr;
+  uint32_t wpc = 4, grid = 0;
+  size_t smem = 0;
+  if (mode == 2) {
+    fn = pick_coop_kernel(g.ld, g.metric);
+    if (!fn) return set_error(COZO_GPU_EUNSUP, "vec_dim %u exceeds the supported maximum 2048", g.dim);
+    const uint32_t cns = std::min<uint32_t>(ns, 3);  // rows in flight per warp; 4 warps share a query
+    ns = cns;
+    p.off_fi = efcap * 4;
+    p.off_pend = p.off_fi + efcap * 4;                 // pend | pdist | ctrl : 128 + 128 + 32 bytes
+    p.off_bars = round_up(p.off_pend + 288, 128);      // start of the per-warp regions
+    p.off_ring = round_up(cns * 8, 128);               // ring offset inside a warp's region
+    p.warp_smem = round_up(p.off_ring + cns * g.ld * 4, 128);
+    smem = (size_t)p.off_bars + (size_t)p.warp_smem * COOP_WARPS;
+    if (smem > di.smem_optin)
+      return set_error(COZO_GPU_EUNSUP, "ef=%u needs %zu B of shared memory per CTA (limit %zu)", ef, smem,
+                       di.smem_optin);
+    COZO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int cps = 0;
+    COZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, fn, 128, smem));
+    if (cps < 1) return set_error(COZO_GPU_ECUDA, "search kernel does not fit on an SM");
+    grid = std::min<uint32_t>((uint32_t)di.sm_count * (uint32_t)cps, B);
+    wpc = 1;  // one visited bitmap / log per CTA
+  } else {
+    const bool bulk = mode != 0;
+    wpc = (uint32_t)get_option("hnsw.warps_per_cta", 4);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 4) wpc = 4;  // __launch_bounds__(128, ..)
+    if (!bulk) ns = 0;
+    fn = pick_kernel(g.ld, g.metric, bulk);
+    if (!fn) return set_error(COZO_GPU_EUNSUP, "vec_dim %u exceeds the supported maximum 2048", g.dim);
+    p.off_fi = efcap * 4;
+    p.off_pend = p.off_fi + efcap * 4;
+    p.off_bars = p.off_pend + 32 * 4;
+    p.off_ring = round_up(p.off_bars + ns * 8, 128);
+    p.warp_smem = round_up(p.off_ring + ns * g.ld * 4, 128);
     smem = (size_t)p.warp_smem * wpc;
+    while (smem > di.smem_optin && wpc > 1) {
+      wpc >>= 1;
+      smem = (size_t)p.warp_smem * wpc;
+    }
+    if (smem > di.smem_optin)
+      return set_error(COZO_GPU_EUNSUP, "ef=%u needs %zu B of shared memory per warp (limit %zu)", ef, smem,
+                       di.smem_optin);
+    COZO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 0;
+    COZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, wpc * 32, smem));
+    if (ctas_per_sm < 1) return set_error(COZO_GPU_ECUDA, "search kernel does not fit on an SM");
+    int64_t cap = get_option("hnsw.max_ctas_per_sm", 0);
+    if (cap > 0 && ctas_per_sm > cap) ctas_per_sm = (int)cap;
+    grid = (uint32_t)di.sm_count * (uint32_t)ctas_per_sm;
+    uint32_t need = (B + wpc - 1) / wpc;
+    if (grid > need) grid = need;
   }
-  if (smem > di.smem_optin)
-    return set_error(COZO_GPU_EUNSUP, "ef=%u needs %zu B of shared memory per warp (limit %zu)", ef, smem,
-                     di.smem_optin);
-  COZO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int ctas_per_sm = 0;
-  COZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, wpc * 32, smem));
-  if (ctas_per_sm < 1) return set_error(COZO_GPU_ECUDA, "search kernel does not fit on an SM");
-  int64_t cap = get_option("hnsw.max_ctas_per_sm", 0);
-  if (cap > 0 && ctas_per_sm > cap) ctas_per_sm = (int)cap;
-  uint32_t grid = (uint32_t)di.sm_count * (uint32_t)ctas_per_sm;
-  uint32_t need = (B + wpc - 1) / wpc;
-  if (grid > need) grid = need;
+  const uint32_t block_threads = mode == 2 ? 128 : wpc * 32;
 
   uint32_t nwords = round_up((g.n + 31) / 32, 4);
   uint32_t logcap = std::min<uint32_t>(65536u, std::max<uint32_t>(4096u, 64u * ef));
@@ -346,7 +499,7 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
     }
   }
   COZO_CUDA(cudaMemsetAsync(ws->counter, 0, 4, stream));
-  fn<<<grid, wpc * 32, smem, stream>>>(g, p);
+  fn<<<grid, block_threads, smem, stream>>>(g, p);
   COZO_CUDA(cudaGetLastError());
   return 0;
 }

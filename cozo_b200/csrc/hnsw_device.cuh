@@ -324,6 +324,129 @@ __device__ __forceinline__ void search_level(const HnswDev& g, WarpCtx& w, const
   visit_clear(w, lane);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cooperative form: ONE CTA (4 warps) per query.  Warp 0 owns the sorted found/candidate array, the
+// visited bitmap and the admission order — exactly the routine above — but the rows of a hop are
+// dealt round-robin to all warps, each with its own bulk-copy ring, and their distances meet in
+// shared memory before warp 0 applies the admissions IN NEIGHBOUR ORDER.  Same traversal, same
+// counters, same results; a query advances ~4x faster, which is what small batches (and the tail of
+// a large one) need: there are not enough queries to fill the SMs with one warp each.
+struct CoopShared {
+  uint32_t* pend;    // [32] unvisited neighbour ids of the current round
+  float* pdist;      // [32] their distances
+  uint32_t* ctrl;    // [0] = number of rows of this round, COOP_DONE = layer finished
+};
+constexpr uint32_t COOP_DONE = 0xFFFFFFFFu;
+constexpr uint32_t COOP_WARPS = 4;
+
+template <int NV, int METRIC>
+__device__ __forceinline__ void coop_search_level(const HnswDev& g, WarpCtx& w, const CoopShared& cs,
+                                                  const float4 (&q)[NV], float qnorm, uint32_t ef, uint32_t level,
+                                                  int lane, int warp) {
+  const int nvec4 = g.ld >> 2;
+  const uint32_t row_bytes = g.ld * 4;
+  const uint32_t stride = level == 0 ? g.s0 : g.su;
+  // warp-0 state of the current expansion
+  const uint32_t* row = nullptr;
+  uint32_t nb = stride;  // chunk offset inside the candidate's adjacency row; stride = need a new candidate
+  if (warp == 0) {
+    for (uint32_t base = 0; base < w.len; base += 32) {  // visited <- keys(found) (hnsw.rs:554-557)
+      uint32_t i = base + lane;
+      uint32_t id = NONE;
+      if (i < w.len) {
+        id = w.fi[i] & IDMASK;
+        w.fi[i] = id;
+      }
+      uint32_t nm;
+      visit_mark(w, id, lane, nm);
+    }
+    __syncwarp();
+    w.cursor = 0;
+  }
+  for (;;) {
+    if (warp == 0) {
+      uint32_t cnt = 0;
+      while (cnt == 0) {
+        if (nb >= stride) {  // candidates.pop() (hnsw.rs:559)
+          uint32_t ci = NONE;
+          for (uint32_t base = w.cursor & ~31u; base < w.len; base += 32) {
+            uint32_t i = base + lane;
+            bool un = (i < w.len) && (i >= w.cursor) && !(w.fi[i] & EXPANDED);
+            uint32_t bal = __ballot_sync(0xffffffffu, un);
+            if (bal) {
+              ci = base + __ffs(bal) - 1;
+              break;
+            }
+          }
+          if (ci == NONE) {
+            cnt = COOP_DONE;
+            break;
+          }
+          uint32_t cand = w.fi[ci];
+          __syncwarp();
+          if (lane == 0) w.fi[ci] = cand | EXPANDED;
+          w.cursor = ci + 1;
+          w.nodes_expanded++;
+          if (level == 0 && ci + 1 + lane < w.len && lane < 2) {
+            uint32_t nxt = w.fi[ci + 1 + lane];
+            if (!(nxt & EXPANDED)) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.adj0 + (size_t)nxt * g.s0));
+          }
+          row = level == 0 ? g.adj0 + (size_t)cand * g.s0
+                           : g.adj_up + (size_t)(g.upper_off[cand] + level - 1) * g.su;
+          nb = 0;
+        }
+        uint32_t id = __ldg(row + nb + lane);
+        uint32_t validmask = __ballot_sync(0xffffffffu, id != NONE);
+        nb = validmask ? nb + 32 : stride;  // rows are packed: an empty chunk ends the row
+        if (!validmask) continue;
+        w.nbr_reads += __popc(validmask);
+        uint32_t newmask;
+        bool isnew = visit_mark(w, id, lane, newmask);
+        cnt = __popc(newmask);
+        if (isnew) cs.pend[__popc(newmask & ((1u << lane) - 1))] = id;
+        w.dist_evals += cnt;
+      }
+      if (lane == 0) cs.ctrl[0] = cnt;
+    }
+    __syncthreads();  // the round's ids are published
+    const uint32_t cnt = cs.ctrl[0];
+    if (cnt == COOP_DONE) break;
+    {  // every warp: rows warp, warp+4, ... through its own ring
+      uint32_t issued = warp, si = w.head, sc = w.head;
+      for (uint32_t c = warp; c < cnt; c += COOP_WARPS) {
+        if (lane == 0) {
+          fence_proxy_async_smem();
+          while (issued < cnt && (issued - c) / COOP_WARPS < w.ns) {
+            mbar_expect_tx(&w.bars[si], row_bytes);
+            bulk_g2s(w.ring + (size_t)si * g.ld, g.vec + (size_t)cs.pend[issued] * g.ld, row_bytes, &w.bars[si]);
+            issued += COOP_WARPS;
+            if (++si == w.ns) si = 0;
+          }
+        }
+        mbar_wait(&w.bars[sc], (w.phase >> sc) & 1u);
+        w.phase ^= (1u << sc);
+        float d = dist_smem<NV, METRIC>(q, reinterpret_cast<const float4*>(w.ring + (size_t)sc * g.ld), lane, nvec4,
+                                        qnorm);
+        if (++sc == w.ns) sc = 0;
+        if (lane == 0) cs.pdist[c] = d;
+        __syncwarp();
+      }
+      w.head = sc;
+    }
+    __syncthreads();  // all distances of the round are in shared memory
+    if (warp == 0) {
+      for (uint32_t c = 0; c < cnt; ++c) {  // hnsw.rs:575-581, in neighbour order with the live bound
+        const float d = cs.pdist[c];
+        const uint32_t nid = cs.pend[c];
+        __syncwarp();
+        if (w.len < ef || d < w.fd[w.len - 1]) sorted_insert(w, ef, d, nid, lane);
+      }
+    }
+  }
+  if (warp == 0) visit_clear(w, lane);
+  __syncthreads();
+}
+
 // load one query into registers (zero padded), optionally its squared norm
 template <int NV>
 __device__ __forceinline__ void load_query(const float* qp, uint32_t dim, int lane, float4 (&q)[NV], float& qnorm) {

@@ -46,14 +46,15 @@ def cfg1(gpu):
     return X, ix, g, Q
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_config1_parity(gpu, cfg1, mode):
+    """mode 0: ld.global rows, 1: warp per query + TMA ring, 2: CTA per query (cooperative)"""
     X, ix, g, Q = cfg1
     gpu.set_option("hnsw.mode", mode)
     try:
         gi, gd, gc, st = g.search(Q, 10, 64)
     finally:
-        gpu.set_option("hnsw.mode", 1)
+        gpu.set_option("hnsw.mode", -1)
     oi, od, oc, ost = ix.search(Q, 10, 64, n_threads=8)
     _compare((gi, gd, gc, st), (oi, od, oc, ost), 10)
     exact = np.mean([set(a) == set(b) for a, b in zip(gi, oi)])
@@ -116,12 +117,12 @@ def test_metrics_and_ragged_dims(gpu, metric, dim, shift):
     X, ix = _oracle_index(n, dim, 8, 60, metric=metric, shift=shift, seed=77 + dim)
     g = _stage(gpu, X, ix.levels(), metric, 8)
     Q = uniform_vectors(200, dim, 78) - np.float32(shift)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         gpu.set_option("hnsw.mode", mode)
         try:
             out = g.search(Q, 10, 80)
         finally:
-            gpu.set_option("hnsw.mode", 1)
+            gpu.set_option("hnsw.mode", -1)
         ref = ix.search(Q, 10, 80, n_threads=8)
         _compare(out, ref, 10, min_recall=0.99)
 
