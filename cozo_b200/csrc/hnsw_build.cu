@@ -650,7 +650,7 @@ int hnsw_insert_range(cozo_gpu_hnsw* h, uint32_t begin, uint32_t end, uint32_t m
   if (!sc.ws) return COZO_GPU_ECUDA;
   HnswWorkspace* ws = sc.ws;
   cudaStream_t st = ws->stream;
-  const uint32_t nwords = round_up((end + 31) / 32, 4);
+  const uint32_t nwords = round_up((g.n + 31) / 32, 4);  // the search may visit ANY indexed id, not only ids < end
   const uint32_t logcap = std::min<uint32_t>(65536u, std::max<uint32_t>(4096u, 64u * ef_c));
   {
     size_t slots = (size_t)max_grid1 * wpc;
@@ -931,6 +931,69 @@ extern "C" int cozo_gpu_hnsw_remove(cozo_gpu_hnsw_t* h, const uint32_t* ids, uin
     g.entry = best;
     g.top_level = best == NONE ? 0 : top;
     h->n_levels = g.top_level + 1;
+  }
+  return 0;
+}
+
+__global__ void clear_dead_kernel(const uint32_t* ids, uint32_t count, uint8_t* dead) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dead[ids[i]] = 0;
+}
+
+// hnsw_put of a CHANGED vector under an existing key (hnsw.rs:175-182: the hash differs, so the old
+// vector is removed and the new one inserted).  The node keeps its id and its layer (the reference
+// draws a fresh level; the level law is the same either way).  Also revives removed ids.
+extern "C" int cozo_gpu_hnsw_update(cozo_gpu_hnsw_t* h, const uint32_t* ids, const float* vectors, uint32_t count,
+                                    uint32_t ef_construction, int32_t keep_pruned_connections) {
+  if (!h || (count && (!ids || !vectors))) return set_error(COZO_GPU_EINVAL, "null argument");
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (count == 0) return 0;
+  HnswDev& g = h->dev;
+  std::vector<uint32_t> order(count);
+  for (uint32_t i = 0; i < count; ++i) {
+    if (ids[i] >= g.n) return set_error(COZO_GPU_EINVAL, "id %u out of range", ids[i]);
+    order[i] = i;
+  }
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b]; });
+  for (uint32_t i = 1; i < count; ++i)
+    if (ids[order[i]] == ids[order[i - 1]]) return set_error(COZO_GPU_EINVAL, "id %u given twice", ids[order[i]]);
+  if (ef_construction) h->ef_construction = ef_construction;
+  if (h->ef_construction == 0) return set_error(COZO_GPU_EINVAL, "ef_construction must be set");
+  if (keep_pruned_connections >= 0) h->keep_pruned = keep_pruned_connections;
+  rc = hnsw_ensure_build_state(h);
+  if (rc) return rc;
+  // 1. drop the old vectors' links (no-op for ids that were already removed)
+  std::vector<uint32_t> live_ids;
+  for (uint32_t i = 0; i < count; ++i)
+    if (h->live[ids[i]]) live_ids.push_back(ids[i]);
+  if (!live_ids.empty()) {
+    rc = cozo_gpu_hnsw_remove(h, live_ids.data(), (uint32_t)live_ids.size());
+    if (rc) return rc;
+  }
+  // 2. new payloads, revive
+  if (!h->vec_owned) {  // never write into a borrowed buffer
+    rc = hnsw_reserve(h, h->borrowed_rows + 1, h->up_rows);
+    if (rc) return rc;
+  }
+  for (uint32_t i = 0; i < count; ++i)
+    H_CUDA(cudaMemcpy(h->d_vec + (size_t)ids[i] * g.ld, vectors + (size_t)i * g.dim, (size_t)g.dim * 4,
+                      cudaMemcpyHostToDevice));
+  uint32_t* d_ids = nullptr;
+  H_CUDA(cudaMalloc(&d_ids, (size_t)count * 4));
+  cudaMemcpy(d_ids, ids, (size_t)count * 4, cudaMemcpyHostToDevice);
+  clear_dead_kernel<<<(count + 255) / 256, 256>>>(d_ids, count, h->d_dead);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(d_ids);
+  if (e != cudaSuccess) return set_error(COZO_GPU_ECUDA, "update failed: %s", cudaGetErrorString(e));
+  for (uint32_t i = 0; i < count; ++i) h->live[ids[i]] = 1;
+  // 3. re-insert, one contiguous id run at a time (hnsw_insert_range links [begin,end) into the graph)
+  for (uint32_t i = 0; i < count;) {
+    uint32_t j = i + 1;
+    while (j < count && ids[order[j]] == ids[order[j - 1]] + 1) ++j;
+    rc = hnsw_insert_range(h, ids[order[i]], ids[order[j - 1]] + 1, 0);
+    if (rc) return rc;
+    i = j;
   }
   return 0;
 }

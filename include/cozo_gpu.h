@@ -162,6 +162,11 @@ int cozo_gpu_hnsw_build(cozo_gpu_hnsw_t** out, const CozoGpuHnswBuildDesc* desc)
 int cozo_gpu_hnsw_insert(cozo_gpu_hnsw_t* h, const float* vectors, uint32_t count, int32_t vectors_on_device,
                          uint32_t ef_construction, int32_t keep_pruned_connections, uint32_t* first_id);
 int cozo_gpu_hnsw_remove(cozo_gpu_hnsw_t* h, const uint32_t* ids, uint32_t count);
+/* hnsw_put of a changed vector under an existing key (hnsw.rs:175-182: remove, then insert again);
+ * vectors [count x dim] host memory, ids distinct.  The node keeps its id and layer.  Removed ids
+ * may be revived this way. */
+int cozo_gpu_hnsw_update(cozo_gpu_hnsw_t* h, const uint32_t* ids, const float* vectors, uint32_t count,
+                         uint32_t ef_construction, int32_t keep_pruned_connections);
 
 /* Read a staged / built index back as per-layer CSR (rows ascending by id). */
 int cozo_gpu_hnsw_info(cozo_gpu_hnsw_t* h, uint32_t* n_vectors, uint32_t* dim, uint32_t* n_levels,

@@ -355,3 +355,33 @@ def test_duplicate_vectors_distance_ties(gpu):
     assert same_group[close].mean() > 0.97
     bi, bd = O.bruteforce_knn(X, Q, 12, n_threads=8)
     assert np.isclose(gd, bd, rtol=1e-5, atol=1e-6).mean() >= np.isclose(od, bd, rtol=1e-5, atol=1e-6).mean() - 0.03
+
+
+def test_update_changed_vectors(gpu):
+    """hnsw_put of a changed vector under an existing key = remove + insert again (hnsw.rs:175-182)"""
+    n, dim, m = 5000, 32, 8
+    X = uniform_vectors(n, dim, 4040)
+    g = gpu.HnswIndex.build(X, m=m, ef_construction=60)
+    ids = np.arange(100, 1100, 2, dtype=np.uint32)               # 500 scattered ids, some adjacent runs none
+    ids = np.concatenate([ids, np.arange(3000, 3050, dtype=np.uint32)])   # plus one contiguous run
+    newv = uniform_vectors(ids.size, dim, 4041)
+    g.update(ids, newv)
+    X2 = X.copy()
+    X2[ids] = newv
+    (ni, rp, ci, ep), view = _export_view(g, X2)
+    deg0 = np.diff(rp[0].astype(np.int64))
+    assert deg0.max() <= 2 * m and deg0[ids].min() >= 1          # the updated rows are linked again
+    out = g.search(newv[:200], 1, 60)
+    assert (out[0][:, 0] == ids[:200]).mean() > 0.95 and np.all(out[1][out[0][:, 0] == ids[:200], 0] == 0)
+    old = g.search(X[ids[:200]], 1, 60)
+    assert not np.any((old[0][:, 0] == ids[:200]) & (old[1][:, 0] == 0))   # the old payloads are gone
+    Q = uniform_vectors(200, dim, 4042)
+    _compare(g.search(Q, 10, 60), view.search(Q, 10, 60, n_threads=8), 10)
+    bi, _ = O.bruteforce_knn(X2, Q, 10, n_threads=8)
+    assert recall(g.search(Q, 10, 60)[0], bi) > 0.85
+    # revive a removed id
+    g.remove(np.array([7], np.uint32))
+    g.update(np.array([7], np.uint32), X[7:8])
+    assert g.search(X[7:8], 1, 60)[0][0, 0] == 7
+    with pytest.raises(gpu.CozoGpuError):
+        g.update(np.array([5, 5], np.uint32), X[:2])
