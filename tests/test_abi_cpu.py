@@ -70,3 +70,42 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not pat.search(txt), f"{f} references the oracle"
+
+
+def _c_prototypes():
+    hdr = open(os.path.join(ROOT, "include", "cozo_gpu.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    out = {}
+    for name, args in re.findall(r"\b(cozo_gpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", body, flags=re.S):
+        args = " ".join(args.split())
+        out[name] = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+    return out
+
+
+def test_rust_ffi_matches_header():
+    """rust/cozo_gpu_sys.rs (the binding a cozo maintainer compiles) declares exactly the header's
+    entry points with the same arity, pointer depth and constness per argument."""
+    src = open(os.path.join(ROOT, "rust", "cozo_gpu_sys.rs")).read()
+    rust = {}
+    for name, args in re.findall(r"pub fn (cozo_gpu_[a-z0-9_]+)\(([^)]*)\)", src):
+        rust[name] = [a.strip() for a in args.split(",")] if args.strip() else []
+    c = _c_prototypes()
+    assert set(rust) == set(c) == set(capi.EXPORTS)
+    for name, cargs in c.items():
+        rargs = rust[name]
+        assert len(rargs) == len(cargs), name
+        for ca, ra in zip(cargs, rargs):
+            cname = re.search(r"([A-Za-z_][A-Za-z_0-9]*)$", ca).group(1)
+            rname, rty = [x.strip() for x in ra.split(":", 1)]
+            assert cname == rname, (name, ca, ra)
+            assert ca.count("*") == rty.count("*"), (name, ca, ra)
+            if "*" in ca:
+                assert ca.startswith("const ") == rty.startswith("*const "), (name, ca, ra)
+    # repr(C) structs carry the same field names in the same order
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "cozo_gpu.h")).read(), flags=re.S)
+    for sname in ("CozoGpuHnswLevel", "CozoGpuHnswStageDesc", "CozoGpuSearchStats", "CozoGpuHnswBuildDesc"):
+        cbody = re.search(r"typedef struct \{([^}]*)\}\s*" + sname + ";", hdr, flags=re.S).group(1)
+        cfields = re.findall(r"([A-Za-z_0-9]+)\s*;", cbody)
+        rbody = re.search(r"pub struct " + sname + r" \{([^}]*)\}", src, flags=re.S).group(1)
+        rfields = re.findall(r"pub ([A-Za-z_0-9]+):", rbody)
+        assert cfields == rfields, sname
