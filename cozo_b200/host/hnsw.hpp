@@ -16,6 +16,8 @@
 #include <optional>
 
 #include "fixed_rule.hpp"
+#include "memcmp.hpp"
+#include "msgpack.hpp"
 
 namespace cozo_host {
 
@@ -52,6 +54,40 @@ struct RelationHandle {
     return it == rows.end() ? nullptr : &it->second;
   }
 };
+
+// The same relation as the storage layer holds it: (key bytes, value bytes) pairs in memcmp order —
+// what StoreTx::range_scan yields for one relation id (storage/mod.rs; runtime/relation.rs:247-296).
+struct KvRelation {
+  uint64_t id = 0;
+  size_t n_keys = 0;
+  std::vector<std::pair<std::string, std::string>> kv;  // ascending key bytes
+
+  // encode_key_for_store / encode_val_for_store over every row of a RelationHandle
+  static KvRelation encode(const RelationHandle& rel, uint64_t id) {
+    KvRelation r;
+    r.id = id;
+    r.n_keys = rel.keys.size();
+    r.kv.reserve(rel.rows.size());
+    for (auto& row : rel.rows)
+      r.kv.emplace_back(memcmp_codec::encode_as_key(row.first, id), msgpack_codec::encode_vals(row.second, r.n_keys, id));
+    std::sort(r.kv.begin(), r.kv.end());  // byte order == value order, so this is a no-op check in practice
+    return r;
+  }
+  // point read: RelationHandle::get (relation.rs:398-417)
+  const std::string* get_val(const Tuple& key) const {
+    const std::string k = memcmp_codec::encode_as_key(key, id);
+    auto it = std::lower_bound(kv.begin(), kv.end(), k,
+                               [](const std::pair<std::string, std::string>& a, const std::string& b) { return a.first < b; });
+    return (it != kv.end() && it->first == k) ? &it->second : nullptr;
+  }
+};
+
+// decode_tuple_from_kv (relation.rs:520-524)
+inline Tuple decode_tuple_from_kv(const std::string& key, const std::string& val) {
+  Tuple t = memcmp_codec::decode_tuple_from_key(key);
+  msgpack_codec::extend_tuple_from_v(t, val);
+  return t;
+}
 
 using CompoundKey = std::tuple<Tuple, size_t, int32_t>;  // hnsw.rs:55
 struct CompoundKeyLess {
@@ -127,10 +163,49 @@ struct StagedHnswIndex {
   //   (layer, fr_k.., fr__field, fr__sub_idx, to_k.., to__field, to__sub_idx, dist, hash, ignore_link)
   // in key order (relation.rs:1064-1126).  K = number of key columns of the base relation.
   void stage(const RelationHandle& base, std::vector<Tuple> idx_rows, const HnswIndexManifest& mf) {
+    stage_with(base.keys.size(), std::move(idx_rows), mf, [&](const CompoundKey& ck, float* out) {
+      const Tuple* row = base.get(std::get<0>(ck));
+      if (!row) throw CozoError("", "Cannot find compound key for HNSW");
+      const DataValue* field = &(*row)[std::get<1>(ck)];
+      if (std::get<2>(ck) >= 0) {
+        if (field->kind != DataValue::List) throw CozoError("", "Cannot interpret " + field->repr() + " as list");
+        field = &field->list[(size_t)std::get<2>(ck)];
+      }
+      if (field->kind != DataValue::Vec || field->v->size() != mf.vec_dim)
+        throw CozoError("", "Cannot interpret " + field->repr() + " as vector");
+      std::copy(field->v->begin(), field->v->end(), out);
+    });
+  }
+
+  // The same, reading both relations from their KV bytes: index keys through the
+  // memcmp codec, `ignore_link` and the vectors through the msgpack value codec, no row materialised
+  // for the base relation (msgpack_codec::extract_vector).
+  void stage_kv(const KvRelation& base, const KvRelation& idx, const HnswIndexManifest& mf) {
+    std::vector<Tuple> idx_rows;
+    idx_rows.reserve(idx.kv.size());
+    for (auto& kv : idx.kv) idx_rows.push_back(decode_tuple_from_kv(kv.first, kv.second));
+    const size_t K = base.n_keys;
+    stage_with(K, std::move(idx_rows), mf, [&](const CompoundKey& ck, float* out) {
+      const std::string* val = base.get_val(std::get<0>(ck));
+      if (!val) throw CozoError("", "Cannot find compound key for HNSW");
+      const size_t fld = std::get<1>(ck);
+      if (fld < K) {  // a vector stored in a key column: decode it from the compound key itself
+        const DataValue& f = std::get<0>(ck)[fld];
+        if (f.kind != DataValue::Vec || f.v->size() != mf.vec_dim)
+          throw CozoError("", "Cannot interpret " + f.repr() + " as vector");
+        std::copy(f.v->begin(), f.v->end(), out);
+        return;
+      }
+      msgpack_codec::extract_vector(*val, fld - K, std::get<2>(ck), out, mf.vec_dim);
+    });
+  }
+
+  // fetch(compound key, out[vec_dim]) = VectorCache::ensure_key (hnsw.rs:122-151)
+  template <class Fetch>
+  void stage_with(size_t K, std::vector<Tuple> idx_rows, const HnswIndexManifest& mf, Fetch fetch) {
     manifest = mf;
     if (mf.dtype_f64)
       throw CozoError("gpu::unsupported", "F64 vector indexes are outside the device envelope (f32 only)");
-    const size_t K = base.keys.size();
     std::sort(idx_rows.begin(), idx_rows.end(), TupleLess());
     // dense ids = compound keys of the layer-0 self-loop rows, in key order
     std::map<CompoundKey, uint32_t, CompoundKeyLess> ids;
@@ -209,18 +284,7 @@ struct StagedHnswIndex {
     }
     // vectors (VectorCache::ensure_key, hnsw.rs:122-151)
     std::vector<float> vectors((size_t)n * mf.vec_dim);
-    for (uint32_t i = 0; i < n; ++i) {
-      const Tuple* row = base.get(std::get<0>(keys[i]));
-      if (!row) throw CozoError("", "Cannot find compound key for HNSW");
-      const DataValue* field = &(*row)[std::get<1>(keys[i])];
-      if (std::get<2>(keys[i]) >= 0) {
-        if (field->kind != DataValue::List) throw CozoError("", "Cannot interpret " + field->repr() + " as list");
-        field = &field->list[(size_t)std::get<2>(keys[i])];
-      }
-      if (field->kind != DataValue::Vec || field->v->size() != mf.vec_dim)
-        throw CozoError("", "Cannot interpret " + field->repr() + " as vector");
-      std::copy(field->v->begin(), field->v->end(), vectors.begin() + (size_t)i * mf.vec_dim);
-    }
+    for (uint32_t i = 0; i < n; ++i) fetch(keys[i], vectors.data() + (size_t)i * mf.vec_dim);
     // flatten to the C ABI descriptor
     std::vector<CozoGpuHnswLevel> levels(n_levels);
     std::vector<std::vector<uint64_t>> row_ptr(n_levels);

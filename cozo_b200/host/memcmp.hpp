@@ -1,8 +1,8 @@
 // memcmp.hpp — the order-preserving key codec of cozo's storage layer (data/memcmp.rs:20-371,
 // data/tuple.rs:22-86), for the value kinds the hot path meets in the keys of `rel:idx` and of the
 // base relation: Null, Bool, Num, Str, Bytes, List, Vec(F32).  This is the KEY half of SURVEY §8f
-// rank 1 ("read the index & base relations straight from KV bytes"); the VALUE half is rmp-serde
-// msgpack whose enum encoding is un-vendored and cannot be verified here.
+// rank 1 ("read the index & base relations straight from KV bytes"); the VALUE half (rmp-serde
+// msgpack, un-vendored, parity unpinned) is msgpack.hpp.
 // Unlike the rest of the host layer this piece is PINNED: data/tests/memcmp.rs's own property
 // tests (round trips, byte order == value order) are reproduced in tests/test_memcmp_cpu.py.
 #pragma once

@@ -131,6 +131,22 @@ struct PyHnswIndex {
     m.derive();
     ix.stage(base.rel, to_rows(idx_rows), m);
   }
+  // the same from KV bytes: lists of (key bytes, value bytes) as a storage range scan yields them
+  void stage_kv(py::handle base_kv, uint64_t base_id, size_t n_keys, py::handle idx_kv, uint64_t idx_id, py::dict mf) {
+    auto load = [](py::handle h, uint64_t id, size_t nk) {
+      KvRelation r;
+      r.id = id;
+      r.n_keys = nk;
+      for (auto item : h) {
+        auto t = item.cast<py::tuple>();
+        r.kv.emplace_back(t[0].cast<std::string>(), t[1].cast<std::string>());
+      }
+      std::sort(r.kv.begin(), r.kv.end());
+      return r;
+    };
+    KvRelation b = load(base_kv, base_id, n_keys), i = load(idx_kv, idx_id, 0);
+    ix.stage_kv(b, i, manifest_of(mf));
+  }
   static HnswIndexManifest manifest_of(py::dict mf) {
     HnswIndexManifest m;
     m.vec_dim = mf["dim"].cast<size_t>();
@@ -220,6 +236,7 @@ PYBIND11_MODULE(_cozo_host, m) {
   py::class_<PyHnswIndex, std::shared_ptr<PyHnswIndex>>(m, "HnswIndex")
       .def(py::init<>())
       .def("stage", &PyHnswIndex::stage)
+      .def("stage_kv", &PyHnswIndex::stage_kv)
       .def("build", &PyHnswIndex::build)
       .def("to_index_rows", &PyHnswIndex::to_index_rows)
       .def("info", &PyHnswIndex::info);
@@ -256,6 +273,47 @@ PYBIND11_MODULE(_cozo_host, m) {
   });
   m.def("memcmp_encode_key", [](py::handle tuple, uint64_t rel) { return py::bytes(memcmp_codec::encode_as_key(to_tuple(tuple), rel)); });
   m.def("memcmp_decode_key", [](py::bytes b) { return from_tuple(memcmp_codec::decode_tuple_from_key(b)); });
+  // msgpack value codec (runtime/relation.rs:275-296, 526-531; rmp-serde 1.2.0 — parity unpinned)
+  m.def("msgpack_encode_value", [](py::handle v) {
+    std::string o;
+    msgpack_codec::encode_datavalue(o, to_dv(v));
+    return py::bytes(o);
+  });
+  m.def("msgpack_decode_value", [](py::bytes b, bool lenient) {
+    std::string s = b;
+    msgpack_codec::Reader r(reinterpret_cast<const uint8_t*>(s.data()), s.size());
+    DataValue v = msgpack_codec::decode_datavalue(r, lenient);
+    return py::make_tuple(from_dv(v), (size_t)(r.p - reinterpret_cast<const uint8_t*>(s.data())));
+  }, py::arg("data"), py::arg("lenient") = true);
+  m.def("msgpack_skip", [](py::bytes b) {
+    std::string s = b;
+    msgpack_codec::Reader r(reinterpret_cast<const uint8_t*>(s.data()), s.size());
+    r.skip();
+    return (size_t)(r.p - reinterpret_cast<const uint8_t*>(s.data()));
+  });
+  m.def("encode_vals", [](py::handle tuple, size_t start, uint64_t rel) {
+    return py::bytes(msgpack_codec::encode_vals(to_tuple(tuple), start, rel));
+  });
+  m.def("decode_tuple_from_kv", [](py::bytes k, py::bytes v) { return from_tuple(decode_tuple_from_kv(k, v)); });
+  m.def("extract_vector", [](py::bytes v, size_t col, int32_t sub, size_t dim) {
+    py::array_t<float> out(dim);
+    msgpack_codec::extract_vector(v, col, sub, out.mutable_data(), dim);
+    return out;
+  });
+  m.def("relation_to_kv", [](const PyRelation& rel, uint64_t id) {
+    KvRelation r = KvRelation::encode(rel.rel, id);
+    py::list out;
+    for (auto& kv : r.kv) out.append(py::make_tuple(py::bytes(kv.first), py::bytes(kv.second)));
+    return out;
+  });
+  m.def("rows_to_kv", [](py::handle rows, size_t n_keys, uint64_t id) {
+    py::list out;
+    for (auto& t : to_rows(rows)) {
+      Tuple k(t.begin(), t.begin() + n_keys);
+      out.append(py::make_tuple(py::bytes(memcmp_codec::encode_as_key(k, id)), py::bytes(msgpack_codec::encode_vals(t, n_keys, id))));
+    }
+    return out;
+  });
   m.def("sha256_le_f32", [](py::array_t<float, py::array::c_style | py::array::forcecast> a) {
     return py::bytes(sha256_le_f32(std::vector<float>(a.data(), a.data() + a.size())));
   });

@@ -322,3 +322,56 @@ def test_build_and_write_back_index_relation(h):
     a = h.HnswSearchRA(base, built, k=5, ef=40, bind_distance=True, bind_idx=0).iter(parent)
     b = h.HnswSearchRA(base, restaged, k=5, ef=40, bind_distance=True, bind_idx=0).iter(parent)
     assert [(r[1], r[3]) for r in a] == [(r[1], r[3]) for r in b] and len(a) == 400
+
+
+def test_stage_from_kv_bytes(h):
+    """the stager reads `rel` and `rel:idx` from their KV bytes (memcmp keys +
+    msgpack values) and lands on the same device index as staging from decoded tuples."""
+    import random
+    dim, m = 16, 4
+    X = uniform_vectors(400, dim, 51)
+    ix = O.OracleHnsw.new(400, dim, m=m, ef_construction=30)
+    ix.insert_all(X)
+    mf = {"dim": dim, "m": m, "ef_construction": 30, "fields": [1]}
+    Q = uniform_vectors(40, dim, 52)
+    # (a) one vector per row, string keys, an extra payload column the stager must step over
+    base = h.Relation("a", ["k"], ["v", "tag", "note"])
+    names = [f"key{i:05d}" for i in range(400)]
+    for i in range(400):
+        base.put([names[i], X[i], i % 7, "n" * (i % 40)])
+    idx_rows = _index_relation(ix, lambda i: [names[i]], 1)
+    # (b) two vectors per row in a list column
+    docs = h.Relation("docs", ["id"], ["chunks"])
+    for r in range(200):
+        docs.put([r, [X[2 * r], X[2 * r + 1]]])
+    layer, fr, to, dist, ign = ix.relation_rows()
+    doc_rows = [[int(l), int(f) // 2, 1, int(f) % 2, int(t) // 2, 1, int(t) % 2, float(d), None, bool(g)]
+                for l, f, t, d, g in zip(layer, fr, to, dist, ign)]
+    doc_rows.append([1, None, None, None, None, None, None, int(layer.min()), b"c", False])
+    for rel, rows, bind in ((base, idx_rows, dict(bind_idx=0)), (docs, doc_rows, dict(bind_idx=0, bind_field_idx=True))):
+        a, b = h.HnswIndex(), h.HnswIndex()
+        a.stage(rel, rows, mf)
+        base_kv = h.relation_to_kv(rel, 11)
+        idx_kv = h.rows_to_kv(rows, 7, 12)                       # 2K+5 key columns, K = 1
+        assert all(k[:8] == (12).to_bytes(8, "big") and v[:8] == (12).to_bytes(8, "big") for k, v in idx_kv)
+        random.Random(5).shuffle(idx_kv)                         # the stager sorts; scan order is not assumed
+        b.stage_kv(base_kv, 11, 1, idx_kv, 12, mf)
+        assert a.info() == b.info()
+        ra = h.HnswSearchRA(rel, a, k=5, ef=30, bind_distance=True, **bind)
+        rb = h.HnswSearchRA(rel, b, k=5, ef=30, bind_distance=True, **bind)
+        oa, ob = ra.iter([[q] for q in Q]), rb.iter([[q] for q in Q])
+        assert len(oa) == len(ob) > 0
+        for x, y in zip(oa, ob):
+            assert len(x) == len(y) and all(_same(p, q) for p, q in zip(x, y))
+    # a truncated value is an error, not a silent zero vector
+    bad = [(k, v[:-3]) for k, v in h.relation_to_kv(base, 11)]
+    with pytest.raises(h.CozoError):
+        h.HnswIndex().stage_kv(bad, 11, 1, h.rows_to_kv(idx_rows, 7, 12), 12, mf)
+
+
+def _same(p, q):
+    if isinstance(p, np.ndarray) or isinstance(q, np.ndarray):
+        return np.array_equal(p, q)
+    if isinstance(p, (list, tuple)):
+        return len(p) == len(q) and all(_same(a, b) for a, b in zip(p, q))
+    return p == q
