@@ -11,6 +11,7 @@
 //   HnswSearchRA::iter                   query/ra.rs:1085-1121
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <functional>
 #include <map>
 #include <optional>
@@ -53,6 +54,7 @@ struct RelationHandle {
     auto it = rows.find(key);
     return it == rows.end() ? nullptr : &it->second;
   }
+  bool erase(const Tuple& key) { return rows.erase(key) > 0; }
 };
 
 // The same relation as the storage layer holds it: (key bytes, value bytes) pairs in memcmp order —
@@ -231,6 +233,8 @@ struct StagedHnswIndex {
       ids.emplace(f, 0u);
     }
     keys.clear();
+    key_ids.clear();
+    live.clear();
     for (auto& kv : ids) {
       kv.second = (uint32_t)keys.size();
       keys.push_back(kv.first);
@@ -334,6 +338,8 @@ struct StagedHnswIndex {
     if (mf.dtype_f64)
       throw CozoError("gpu::unsupported", "F64 vector indexes are outside the device envelope (f32 only)");
     keys.clear();
+    key_ids.clear();
+    live.clear();
     std::vector<float> vectors;
     for (auto& kv : base.rows) {
       for (size_t fld : mf.vec_fields) {
@@ -393,6 +399,160 @@ struct StagedHnswIndex {
     d.keep_pruned_connections = mf.keep_pruned_connections;
     d.level_seed = level_seed;
     gpu_check(cozo_gpu_hnsw_build(&h, &d));
+  }
+
+  // ---- maintenance: `:put` / `:rm` on an indexed relation (query/stored.rs:332, 995-997) -------------
+  // The device copy absorbs a mutation in place when dense ids can stay in compound-key order (the order
+  // the entry-point rule reads, hnsw.rs:891-899): changed vectors under existing keys, removals, and new
+  // rows whose key sorts after every indexed key (the append case).  Anything else re-indexes from the
+  // base relation (`rebuilt` counts those).
+  std::map<CompoundKey, uint32_t, CompoundKeyLess> key_ids;  // compound key -> dense id (lazily rebuilt)
+  std::vector<uint8_t> live;                                  // host mirror of the device's live flags
+  uint64_t n_put_unchanged = 0, n_put_updated = 0, n_put_appended = 0, n_removed = 0, n_rebuilt = 0;
+
+  void sync_dictionary() {
+    if (key_ids.size() == keys.size() && live.size() == keys.size()) return;
+    key_ids.clear();
+    for (uint32_t i = 0; i < keys.size(); ++i) key_ids.emplace(keys[i], i);
+    live.assign(keys.size(), 1);
+    if (!keys.empty()) gpu_check(cozo_gpu_hnsw_export_live(h, live.data()));
+  }
+
+  // the (vector, field, sub_idx) triples hnsw_put extracts from a row (hnsw.rs:694-706)
+  std::vector<std::tuple<const std::vector<float>*, size_t, int32_t>> extract_vectors(const Tuple& tuple) const {
+    std::vector<std::tuple<const std::vector<float>*, size_t, int32_t>> out;
+    for (size_t fld : manifest.vec_fields) {
+      const DataValue& val = tuple.at(fld);
+      if (val.kind == DataValue::Vec) out.emplace_back(val.v.get(), fld, -1);
+      else if (val.kind == DataValue::List)
+        for (size_t i = 0; i < val.list.size(); ++i)
+          if (val.list[i].kind == DataValue::Vec) out.emplace_back(val.list[i].v.get(), fld, (int32_t)i);
+    }
+    return out;
+  }
+
+  // SessionTx::hnsw_remove (hnsw.rs:728-753) for a batch of rows: every indexed vector of each row
+  void remove_rows(RelationHandle& base, const std::vector<Tuple>& rows) {
+    sync_dictionary();
+    const size_t K = base.keys.size();
+    std::vector<uint32_t> ids;
+    for (const Tuple& row : rows) {
+      Tuple key(row.begin(), row.begin() + K);
+      for (auto it = key_ids.lower_bound(CompoundKey(key, 0, INT32_MIN));
+           it != key_ids.end() && cmp_tuple(std::get<0>(it->first), key) == 0; ++it)
+        if (live[it->second]) {
+          ids.push_back(it->second);
+          live[it->second] = 0;
+        }
+      base.erase(key);
+    }
+    if (!ids.empty()) gpu_check(cozo_gpu_hnsw_remove(h, ids.data(), (uint32_t)ids.size()));
+    n_removed += ids.size();
+  }
+
+  // SessionTx::hnsw_put (hnsw.rs:679-727) for a batch of rows, then the rows go into the base relation.
+  // `filter` is the index_filter predicate (rows failing it are un-indexed, hnsw.rs:688-693).
+  void put_rows(RelationHandle& base, const std::vector<Tuple>& all_rows,
+                const std::function<bool(const Tuple&)>& filter = nullptr) {
+    sync_dictionary();
+    const size_t K = base.keys.size(), dim = manifest.vec_dim;
+    // several rows under one key in a batch: the reference applies them in order, so the last one stands
+    std::vector<Tuple> rows;
+    {
+      std::map<Tuple, size_t, TupleLess> last;
+      for (size_t i = 0; i < all_rows.size(); ++i) {
+        if (all_rows[i].size() < K) throw CozoError("", "row arity mismatch");
+        last[Tuple(all_rows[i].begin(), all_rows[i].begin() + K)] = i;
+      }
+      for (size_t i = 0; i < all_rows.size(); ++i)
+        if (last[Tuple(all_rows[i].begin(), all_rows[i].begin() + K)] == i) rows.push_back(all_rows[i]);
+    }
+    std::vector<uint32_t> upd_ids, rm_ids;
+    std::vector<float> upd_vecs;
+    std::vector<std::pair<CompoundKey, const std::vector<float>*>> appended;
+    for (const Tuple& row : rows) {
+      if (row.size() != base.keys.size() + base.non_keys.size()) throw CozoError("", "row arity mismatch");
+      Tuple key(row.begin(), row.begin() + K);
+      if (filter && !filter(row)) {  // hnsw.rs:688-693
+        for (auto it = key_ids.lower_bound(CompoundKey(key, 0, INT32_MIN));
+             it != key_ids.end() && cmp_tuple(std::get<0>(it->first), key) == 0; ++it)
+          if (live[it->second]) {
+            rm_ids.push_back(it->second);
+            live[it->second] = 0;
+          }
+        continue;
+      }
+      const Tuple* old_row = base.get(key);
+      for (auto& [vec, fld, sub] : extract_vectors(row)) {
+        if (vec->size() != dim) throw CozoError("", "vector dimension mismatch for the index");
+        CompoundKey ck(key, fld, sub);
+        auto it = key_ids.find(ck);
+        if (it == key_ids.end()) {
+          appended.emplace_back(std::move(ck), vec);
+          continue;
+        }
+        if (live[it->second] && old_row) {  // same bytes under the same key: nothing to do (hnsw.rs:175-179)
+          const DataValue* f = &(*old_row)[fld];
+          if (sub >= 0 && f->kind == DataValue::List && (size_t)sub < f->list.size()) f = &f->list[(size_t)sub];
+          if (f->kind == DataValue::Vec && f->v->size() == dim &&
+              std::memcmp(f->v->data(), vec->data(), dim * sizeof(float)) == 0) {
+            n_put_unchanged++;
+            continue;
+          }
+        }
+        upd_ids.push_back(it->second);  // remove + insert again (hnsw.rs:180-182)
+        upd_vecs.insert(upd_vecs.end(), vec->begin(), vec->end());
+        live[it->second] = 1;
+      }
+    }
+    std::sort(appended.begin(), appended.end(),
+              [](const auto& a, const auto& b) { return CompoundKeyLess()(a.first, b.first); });
+    const bool in_order = appended.empty() || key_ids.empty() || CompoundKeyLess()(key_ids.rbegin()->first, appended.front().first);
+    for (const Tuple& row : rows) base.put(row);
+    if (!in_order) {  // a new key lands inside the indexed key range: re-index (ids must stay in key order)
+      n_rebuilt++;
+      build(base, manifest);
+      if (filter) {
+        std::vector<Tuple> drop;
+        for (auto& kv : base.rows)
+          if (!filter(kv.second)) drop.push_back(kv.second);
+        // un-index without deleting the rows
+        sync_dictionary();
+        std::vector<uint32_t> ids;
+        for (const Tuple& row : drop) {
+          Tuple key(row.begin(), row.begin() + K);
+          for (auto it = key_ids.lower_bound(CompoundKey(key, 0, INT32_MIN));
+               it != key_ids.end() && cmp_tuple(std::get<0>(it->first), key) == 0; ++it)
+            if (live[it->second]) {
+              ids.push_back(it->second);
+              live[it->second] = 0;
+            }
+        }
+        if (!ids.empty()) gpu_check(cozo_gpu_hnsw_remove(h, ids.data(), (uint32_t)ids.size()));
+      }
+      return;
+    }
+    if (!rm_ids.empty()) gpu_check(cozo_gpu_hnsw_remove(h, rm_ids.data(), (uint32_t)rm_ids.size()));
+    n_removed += rm_ids.size();
+    if (!upd_ids.empty())
+      gpu_check(cozo_gpu_hnsw_update(h, upd_ids.data(), upd_vecs.data(), (uint32_t)upd_ids.size(),
+                                     (uint32_t)manifest.ef_construction, manifest.keep_pruned_connections ? 1 : 0));
+    n_put_updated += upd_ids.size();
+    if (!appended.empty()) {
+      std::vector<float> flat;
+      flat.reserve(appended.size() * dim);
+      for (auto& a : appended) flat.insert(flat.end(), a.second->begin(), a.second->end());
+      uint32_t first = 0;
+      gpu_check(cozo_gpu_hnsw_insert(h, flat.data(), (uint32_t)appended.size(), 0, (uint32_t)manifest.ef_construction,
+                                     manifest.keep_pruned_connections ? 1 : 0, &first));
+      if (first != keys.size()) throw CozoError("", "device ids out of step with the key dictionary");
+      for (auto& a : appended) {
+        key_ids.emplace(a.first, (uint32_t)keys.size());
+        keys.push_back(a.first);
+        live.push_back(1);
+      }
+      n_put_appended += appended.size();
+    }
   }
 
   // The rows of `rel:idx` (runtime/relation.rs:1064-1126) that describe the device

@@ -163,6 +163,12 @@ struct PyHnswIndex {
     return m;
   }
   void build(const PyRelation& base, py::dict mf) { ix.build(base.rel, manifest_of(mf)); }
+  void put_rows(PyRelation& base, py::handle rows, py::object filter) {
+    std::function<bool(const Tuple&)> f;
+    if (!filter.is_none()) f = [filter](const Tuple& t) { return filter(from_tuple(t)).cast<bool>(); };
+    ix.put_rows(base.rel, to_rows(rows), f);
+  }
+  void remove_rows(PyRelation& base, py::handle rows) { ix.remove_rows(base.rel, to_rows(rows)); }
   py::list to_index_rows(const PyRelation& base) const { return from_rows(ix.to_index_rows(base.rel)); }
   py::dict info() const {
     py::dict d;
@@ -170,6 +176,11 @@ struct PyHnswIndex {
     d["edges_kept"] = ix.n_edges_kept;
     d["dropped_same_key"] = ix.n_rows_dropped_same_key;
     d["dropped_ignore_link"] = ix.n_rows_dropped_ignored;
+    d["put_unchanged"] = ix.n_put_unchanged;
+    d["put_updated"] = ix.n_put_updated;
+    d["put_appended"] = ix.n_put_appended;
+    d["removed"] = ix.n_removed;
+    d["rebuilt"] = ix.n_rebuilt;
     return d;
   }
 };
@@ -238,6 +249,8 @@ PYBIND11_MODULE(_cozo_host, m) {
       .def("stage", &PyHnswIndex::stage)
       .def("stage_kv", &PyHnswIndex::stage_kv)
       .def("build", &PyHnswIndex::build)
+      .def("put_rows", &PyHnswIndex::put_rows, py::arg("base"), py::arg("rows"), py::arg("filter") = py::none())
+      .def("remove_rows", &PyHnswIndex::remove_rows)
       .def("to_index_rows", &PyHnswIndex::to_index_rows)
       .def("info", &PyHnswIndex::info);
   py::class_<PyHnswSearchRA>(m, "HnswSearchRA")

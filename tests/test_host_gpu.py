@@ -363,8 +363,8 @@ def test_stage_from_kv_bytes(h):
         assert len(oa) == len(ob) > 0
         for x, y in zip(oa, ob):
             assert len(x) == len(y) and all(_same(p, q) for p, q in zip(x, y))
-    # a truncated value is an error, not a silent zero vector
-    bad = [(k, v[:-3]) for k, v in h.relation_to_kv(base, 11)]
+    # a value cut inside the vector column is an error, not a silent zero vector
+    bad = [(k, v[:40]) for k, v in h.relation_to_kv(base, 11)]
     with pytest.raises(h.CozoError):
         h.HnswIndex().stage_kv(bad, 11, 1, h.rows_to_kv(idx_rows, 7, 12), 12, mf)
 
@@ -375,3 +375,70 @@ def _same(p, q):
     if isinstance(p, (list, tuple)):
         return len(p) == len(q) and all(_same(a, b) for a, b in zip(p, q))
     return p == q
+
+
+def test_put_and_rm_on_an_indexed_relation(h):
+    """`:put` / `:rm` on a relation with an HNSW index (query/stored.rs:332, 995-997 → hnsw_put /
+    hnsw_remove, hnsw.rs:679-753), absorbed by the device copy."""
+    n, dim, m = 1200, 24, 8
+    X = uniform_vectors(n + 400, dim, 71)
+    mf = {"dim": dim, "m": m, "ef_construction": 60, "fields": [1]}
+    names = [f"key{i:05d}" for i in range(n + 400)]
+    base = h.Relation("a", ["k"], ["v", "tag"])
+    for i in range(n):
+        base.put([names[i], X[i], i])
+    index = h.HnswIndex()
+    index.build(base, mf)
+
+    def top1(vectors):
+        out = h.HnswSearchRA(base, index, k=1, ef=80, bind_distance=True, bind_idx=0).iter([[v] for v in vectors])
+        return [(r[1], r[4]) for r in out]                              # (key, distance), one per query
+
+    def all_keys(vectors, k=10):
+        out = h.HnswSearchRA(base, index, k=k, ef=80, bind_idx=0).iter([[v] for v in vectors])
+        return {r[1] for r in out}
+
+    # (1) the same vector under the same key: no device work (hnsw.rs:175-179); the payload column still changes
+    index.put_rows(base, [[names[5], X[5], 99]])
+    info = index.info()
+    assert (info["put_unchanged"], info["put_updated"], info["put_appended"]) == (1, 0, 0)
+    # (2) append: keys after every indexed key
+    index.put_rows(base, [[names[i], X[i], i] for i in range(n, n + 200)])
+    info = index.info()
+    assert info["put_appended"] == 200 and info["rebuilt"] == 0 and len(base) == n + 200
+    hits = top1(X[n:n + 200])
+    assert sum(k == names[n + i] and d == 0.0 for i, (k, d) in enumerate(hits)) >= 190
+    # (3) a changed vector under an existing key = remove + insert again (hnsw.rs:180-182)
+    index.put_rows(base, [[names[i], X[n + 200 + i], i] for i in range(50)])
+    assert index.info()["put_updated"] == 50
+    hits = top1(X[n + 200:n + 250])
+    assert sum(k == names[i] and d == 0.0 for i, (k, d) in enumerate(hits)) >= 47
+    assert all(d > 0.0 for _, d in top1(X[:50]))                        # the old vectors are gone
+    # (4) :rm
+    gone = [names[i] for i in range(100, 160)]
+    index.remove_rows(base, [[g] for g in gone])
+    assert index.info()["removed"] == 60 and len(base) == n + 200 - 60
+    assert not (all_keys(X[100:160]) & set(gone))
+    # (5) a removed key comes back
+    index.put_rows(base, [[names[100], X[100], 100]])
+    assert top1(X[100:101])[0] == (names[100], 0.0)
+    # (6) index_filter: a row failing it is stored but not indexed (hnsw.rs:688-693)
+    keep = lambda r: r[2] >= 0
+    index.put_rows(base, [[names[200], X[200], -1]], filter=keep)
+    assert names[200] not in all_keys(X[200:201]) and len(base) == n + 200 - 60 + 1
+    # (7) a new key INSIDE the indexed key range: the device copy re-indexes, ids stay in key order
+    index.put_rows(base, [["key00000a", X[n + 300], 7], [names[n + 399], X[n + 399], 8]], filter=keep)
+    assert index.info()["rebuilt"] == 1
+    assert top1(X[n + 300:n + 301])[0] == ("key00000a", 0.0)
+    assert names[200] not in all_keys(X[200:201])
+    # (8) two rows under one key in a batch: the last one stands
+    index.put_rows(base, [[names[300], X[n + 310], 1], [names[300], X[n + 311], 2]], filter=keep)
+    assert top1(X[n + 311:n + 312])[0] == (names[300], 0.0) and top1(X[n + 310:n + 311])[0][1] > 0.0
+    # write the maintained index back as rows of `rel:idx`, re-stage from them: same answers
+    rows = index.to_index_rows(base)
+    fresh = h.HnswIndex()
+    fresh.stage(base, rows, mf)
+    Q = uniform_vectors(60, dim, 72)
+    a = h.HnswSearchRA(base, index, k=5, ef=40, bind_distance=True, bind_idx=0).iter([[q] for q in Q])
+    b = h.HnswSearchRA(base, fresh, k=5, ef=40, bind_distance=True, bind_idx=0).iter([[q] for q in Q])
+    assert [(r[1], r[4]) for r in a] == [(r[1], r[4]) for r in b] and len(a) == 300
