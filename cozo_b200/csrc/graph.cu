@@ -20,27 +20,33 @@ struct cozo_gpu_graph {
   bool weighted = false;
   uint32_t *out_ptr = nullptr, *out_idx = nullptr, *in_ptr = nullptr, *in_idx = nullptr;
   float* out_w = nullptr;
-  uint32_t* hubs = nullptr;  // rows with in-degree > HUB_T
+  // ---- PageRank works on a RELABELLED copy of the in-CSR ("slot space") --------------------------
+  // slot[v] = rank of v by out-degree, descending.  A source is gathered once per out-edge, so in
+  // slot space the few ten-thousand sources that carry almost half of an R-MAT graph's edges are the
+  // first entries of the contribution vector: the pull kernel keeps them in shared memory.  Rows are
+  // processed in slot order (scores, contributions and out-degrees are all slot-indexed: coalesced,
+  // no scatter), and each row's in-neighbours are sorted by slot, so neighbouring lanes tend to
+  // touch the same cache line.  Scores are un-permuted once, when the result is copied out.
+  uint32_t *slot = nullptr;                                 // [n]   original id -> slot
+  uint32_t *pr_in_ptr = nullptr, *pr_in_idx = nullptr;      // in-CSR in slot space ([n+1], [m])
+  uint32_t *pr_od = nullptr;                                // [n]   out-degree by slot
+  uint32_t* hubs = nullptr;  // slot-space rows with in-degree > HUB_T
   uint32_t n_hubs = 0;
   uint32_t* blk_start = nullptr;  // [2*n_blk] row mini-blocks [r0,r1) of the pull kernel (<=32 rows, <=256 in-edges)
   uint32_t n_blk = 0;
   uint32_t* med_rows = nullptr;   // rows with BLK_CAP < in-degree <= HUB_T: one warp each
   uint32_t n_med = 0;
-  // PageRank keeps its contribution vector in "hot-first" order: slot[v] = rank of v by out-degree
-  // (descending), in_idx_hot = slot[in_idx].  A source is gathered once per out-edge, so the few
-  // thousand hub sources that carry most of the edges share a few hundred cache lines (L1-resident).
-  uint32_t *slot = nullptr, *in_idx_hot = nullptr;
-  // hub rows are cut into chunks of <= HUB_CHUNK in-edges, one CTA per chunk
+  // hub rows are cut into chunks of <= HUB_CHUNK in-edges, one warp per chunk
   uint32_t *hub_chunk_ptr = nullptr, *chunk_beg = nullptr, *chunk_end = nullptr;
   uint32_t n_chunks = 0;
 };
 
 namespace cozo {
 
-constexpr uint32_t HUB_T = 4096;   // rows longer than this are cut into HUB_CHUNK pieces, one CTA each
+constexpr uint32_t HUB_T = 4096;   // rows longer than this are cut into HUB_CHUNK pieces, one warp each
 constexpr uint32_t BLK_CAP = 256;  // in-edges of a warp's mini-block (8 gathers per lane in flight)
 constexpr uint32_t BLK_ROWS = 32;  // rows per mini-block: one lane sums one row
-constexpr uint32_t HUB_CHUNK = 4096; // in-edges of a hub row summed by one CTA
+constexpr uint32_t HUB_CHUNK = 4096; // in-edges of a hub row summed by one warp
 
 __global__ void edge_check_kernel(const uint32_t* src, const uint32_t* dst, const float* w, uint64_t m, uint32_t n,
                                   int* bad) {
@@ -78,26 +84,18 @@ __global__ void iota_kernel(uint32_t* p, uint64_t m) {
   if (e < m) p[e] = (uint32_t)e;
 }
 
-__global__ void find_hubs_kernel(const uint32_t* in_ptr, uint32_t n, uint32_t* hubs, uint32_t* n_hubs) {
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= n) return;
-  if (in_ptr[u + 1] - in_ptr[u] > HUB_T) hubs[atomicAdd(n_hubs, 1u)] = u;
-}
-
 // ---- PageRank ----------------------------------------------------------------
 // GAP-style pull iteration (graph 0.3.1 page_rank, un-vendored):
 //   new[u] = base + d * sum_{v in in(u)} contrib[v];  err += |new[u]-old[u]| (f64)
 //   contrib'[u] = new[u] / out_degree(u)
-// 8 lanes per destination row; rows longer than HUB_T go to the hub kernel.
-__global__ void pr_init_kernel(const uint32_t* out_ptr, const uint32_t* slot, uint32_t n, float init, float* scores,
-                               float* contrib) {
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= n) return;
-  scores[u] = init;
-  uint32_t od = out_ptr[u + 1] - out_ptr[u];
-  contrib[slot[u]] = od ? init / (float)od : 0.f;  // od==0: value is never read (no out edge leads anywhere)
+// Everything below is indexed in slot space (see struct cozo_gpu_graph).
+__global__ void pr_init_kernel(const uint32_t* __restrict__ od, uint32_t n, float init, float* scores, float* contrib) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  scores[r] = init;
+  const uint32_t d = od[r];
+  contrib[r] = d ? init / (float)d : 0.f;  // d==0: value is never read (no out edge leads anywhere)
 }
-
 __global__ void pr_slot_kernel(const uint32_t* perm, uint32_t n, uint32_t* slot) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n) slot[perm[r]] = r;
@@ -109,9 +107,28 @@ __global__ void pr_degkey_kernel(const uint32_t* out_ptr, uint32_t n, uint32_t* 
     val[u] = u;
   }
 }
-__global__ void pr_relabel_kernel(const uint32_t* in_idx, const uint32_t* slot, uint64_t m, uint32_t* out) {
-  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < m) out[e] = slot[in_idx[e]];
+// per original row u: degrees by slot
+__global__ void pr_degrees_kernel(const uint32_t* out_ptr, const uint32_t* in_ptr, const uint32_t* slot, uint32_t n,
+                                  uint32_t* od_slot, uint32_t* in_cnt_slot) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  const uint32_t r = slot[u];
+  od_slot[r] = out_ptr[u + 1] - out_ptr[u];
+  in_cnt_slot[r] = in_ptr[u + 1] - in_ptr[u];
+}
+// one warp per original destination row: key = (slot[dst] << 32) | slot[src] for each in-edge
+__global__ void pr_edge_keys_kernel(const uint32_t* __restrict__ in_ptr, const uint32_t* __restrict__ in_idx,
+                                    const uint32_t* __restrict__ slot, uint32_t n, unsigned long long* keys) {
+  const uint32_t w = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const unsigned long long hi = (unsigned long long)slot[w] << 32;
+  for (uint32_t e = in_ptr[w] + lane; e < in_ptr[w + 1]; e += 32) keys[e] = hi | slot[in_idx[e]];
+}
+__global__ void pr_unpermute_kernel(const float* __restrict__ scores_slot, const uint32_t* __restrict__ slot, uint32_t n,
+                                    float* out) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < n) out[u] = scores_slot[slot[u]];
 }
 
 __device__ __forceinline__ void block_add_err(double e, double* out) {
@@ -151,141 +168,143 @@ __device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t* a, uint64_t pol
   return v;
 }
 
-// CSR-stream pull at warp granularity.  A warp owns a mini-block of <= 32 consecutive destination
-// rows with <= 256 in-edges in total.  Phase 1: the in_idx slice is read coalesced (L2 evict-first)
-// and every lane issues up to 8 independent gathers of contrib[v] (L2 evict-last: the 4N-byte
-// vector is asked to stay in L2) before the first use, staging the values in the warp's 1 KB of
-// shared memory; phase 2: lane l sums row l's slice IN IN-NEIGHBOUR ORDER, the order
-// `.sum::<f32>()` uses in graph::page_rank, so these rows match a sequential CPU run bit for bit.
-// No block-wide barrier anywhere: 64 independent warp pipelines per SM.
-__global__ void __launch_bounds__(256) pr_iter_kernel(const uint32_t* __restrict__ blk_start, uint32_t n_blk,
-                                                      const uint32_t* __restrict__ in_ptr,
-                                                      const uint32_t* __restrict__ in_idx,
-                                                      const uint32_t* __restrict__ out_ptr,
-                                                      const uint32_t* __restrict__ slot, float base, float damping,
-                                                      const float* __restrict__ contrib_old,
-                                                      float* __restrict__ contrib_new, float* __restrict__ scores,
-                                                      double* err) {
-  __shared__ float vals_all[8][BLK_CAP];
+struct PrArgs {
+  const uint32_t *in_ptr, *in_idx, *od;            // slot-space in-CSR and out-degrees
+  const uint32_t *blk_start, *med_rows, *chunk_beg, *chunk_end;
+  uint32_t n_blk, n_med, n_chunks;
+  uint32_t dynamic;                                // 1: warps draw work items from device counters
+  float base, damping;
+  const float* contrib_old;
+  float *contrib_new, *scores, *partial;
+  double* err;                                     // err[0]; the three work counters follow at err + 1
+};
+
+// a warp sums contrib over in_idx[b, en): 8 independent gathers per lane in flight, shuffle tree
+__device__ __forceinline__ float pr_warp_row_sum(const PrArgs& a, uint32_t b, uint32_t en, int lane, uint64_t keep,
+                                                 uint64_t stream) {
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint32_t k = b + lane;
+  for (; k + 224 < en; k += 256) {
+    uint32_t i[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) i[j] = ldg_u32_hint(a.in_idx + k + 32 * j, stream);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += ldg_f32_hint(a.contrib_old + i[j], keep);
+  }
+  for (; k < en; k += 32) s[0] += ldg_f32_hint(a.contrib_old + ldg_u32_hint(a.in_idx + k, stream), keep);
+  return warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
+}
+
+// work distribution of the pull kernel: static round-robin over warps, or `batch` consecutive items
+// at a time from a device counter (one atomic per batch, lane 0, broadcast)
+struct PrCursor {
+  uint32_t cur, end, stride;
+};
+__device__ __forceinline__ bool pr_next(PrCursor& c, uint32_t n_items, uint32_t* ctr, uint32_t batch, bool dynamic,
+                                        int lane) {
+  if (!dynamic) {
+    if (c.cur >= n_items) return false;
+    c.end = c.cur + 1;  // one item; the caller advances by stride
+    return true;
+  }
+  uint32_t v = 0;
+  if (lane == 0) v = atomicAdd(ctr, batch);
+  v = __shfl_sync(0xffffffffu, v, 0);
+  if (v >= n_items) return false;
+  c.cur = v;
+  c.end = min(v + batch, n_items);
+  return true;
+}
+
+// The pull iteration: ONE persistent launch.
+//   phase 1   hub chunks (<= 4096 in-edges of a row with in-degree > HUB_T): one warp per chunk writes
+//             a partial sum; pr_hub_final_kernel adds a row's partials in chunk order afterwards
+//   phase 2   medium rows (BLK_CAP < in-degree <= HUB_T): one warp per row
+//   phase 3   CSR-stream at warp granularity: a warp owns a mini-block of <= 32 consecutive rows with
+//             <= 256 in-edges in total; the in_idx slice is read coalesced (L2 evict-first), every lane
+//             issues up to 8 independent gathers (L2 evict-last: the 4N-byte vector is asked to stay in
+//             L2) before the first use and stages the values in the warp's 1 KB of shared memory; then
+//             lane l sums row l's slice in stored (slot) order.
+// Heavy items first, so the tail of the launch is made of the smallest work items.  No block-wide
+// barrier before the final error reduction: independent warp pipelines.
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pr_pull_kernel(const PrArgs a) {
+  __shared__ float vals_all[WARPS][BLK_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* vals = vals_all[warp];
   const uint64_t keep = l2_policy_evict_last();
   const uint64_t stream = l2_policy_evict_first();
-  const uint32_t wglobal = blockIdx.x * 8 + warp, wtotal = gridDim.x * 8;
+  const uint32_t wglobal = blockIdx.x * WARPS + warp, wtotal = gridDim.x * WARPS;
+  const bool dyn = a.dynamic != 0;
+  uint32_t* ctr = reinterpret_cast<uint32_t*>(a.err + 1);
   double e = 0.0;
-  for (uint32_t blk = wglobal; blk < n_blk; blk += wtotal) {
-    const uint32_t r0 = blk_start[2 * blk], r1 = blk_start[2 * blk + 1];
-    const uint32_t nrows = r1 - r0;
-    uint32_t lo = 0, hi = 0;
-    if ((uint32_t)lane < nrows) {
-      lo = in_ptr[r0 + lane];
-      hi = in_ptr[r0 + lane + 1];
+  PrCursor c{wglobal, 0, wtotal};
+  while (pr_next(c, a.n_chunks, ctr + 0, 1, dyn, lane)) {
+    for (uint32_t i = c.cur; i < c.end; ++i) {
+      const float s = pr_warp_row_sum(a, a.chunk_beg[i], a.chunk_end[i], lane, keep, stream);
+      if (lane == 0) a.partial[i] = s;
     }
-    const uint32_t e0 = __shfl_sync(0xffffffffu, lo, 0);
-    const uint32_t e1 = __shfl_sync(0xffffffffu, hi, nrows - 1);
-    uint32_t idx[8];
+    c.cur += c.stride;
+  }
+  c = PrCursor{wglobal, 0, wtotal};
+  while (pr_next(c, a.n_med, ctr + 1, 2, dyn, lane)) {
+    for (uint32_t i = c.cur; i < c.end; ++i) {
+      const uint32_t r = a.med_rows[i];
+      const float s = pr_warp_row_sum(a, a.in_ptr[r], a.in_ptr[r + 1], lane, keep, stream);
+      if (lane == 0) {
+        const float nw = a.base + a.damping * s;
+        e += (double)fabsf(nw - a.scores[r]);
+        a.scores[r] = nw;
+        const uint32_t od = a.od[r];
+        a.contrib_new[r] = od ? nw / (float)od : 0.f;
+      }
+    }
+    c.cur += c.stride;
+  }
+  c = PrCursor{wglobal, 0, wtotal};
+  while (pr_next(c, a.n_blk, ctr + 2, 8, dyn, lane)) {
+    for (uint32_t blk = c.cur; blk < c.end; ++blk) {
+      const uint32_t r0 = a.blk_start[2 * blk], r1 = a.blk_start[2 * blk + 1];
+      const uint32_t nrows = r1 - r0;
+      uint32_t lo = 0, hi = 0;
+      if ((uint32_t)lane < nrows) {
+        lo = a.in_ptr[r0 + lane];
+        hi = a.in_ptr[r0 + lane + 1];
+      }
+      const uint32_t e0 = __shfl_sync(0xffffffffu, lo, 0);
+      const uint32_t e1 = __shfl_sync(0xffffffffu, hi, nrows - 1);
+      uint32_t idx[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t k = e0 + lane + 32 * j;
-      idx[j] = k < e1 ? ldg_u32_hint(in_idx + k, stream) : NONE;
-    }
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t k = e0 + lane + 32 * j;
+        idx[j] = k < e1 ? ldg_u32_hint(a.in_idx + k, stream) : NONE;
+      }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) vals[lane + 32 * j] = idx[j] != NONE ? ldg_f32_hint(contrib_old + idx[j], keep) : 0.f;
-    __syncwarp();
-    if ((uint32_t)lane < nrows) {
-      const uint32_t r = r0 + lane;
-      float s = 0.f;
-      for (uint32_t j = lo - e0; j < hi - e0; ++j) s += vals[j];
-      const float nw = base + damping * s;
-      e += (double)fabsf(nw - scores[r]);
-      scores[r] = nw;
-      const uint32_t od = out_ptr[r + 1] - out_ptr[r];
-      contrib_new[slot[r]] = od ? nw / (float)od : 0.f;
+      for (int j = 0; j < 8; ++j) vals[lane + 32 * j] = idx[j] != NONE ? ldg_f32_hint(a.contrib_old + idx[j], keep) : 0.f;
+      __syncwarp();
+      if ((uint32_t)lane < nrows) {
+        const uint32_t r = r0 + lane;
+        float s = 0.f;
+        for (uint32_t j = lo - e0; j < hi - e0; ++j) s += vals[j];
+        const float nw = a.base + a.damping * s;
+        e += (double)fabsf(nw - a.scores[r]);
+        a.scores[r] = nw;
+        const uint32_t od = a.od[r];
+        a.contrib_new[r] = od ? nw / (float)od : 0.f;
+      }
+      __syncwarp();
     }
-    __syncwarp();
+    c.cur += c.stride;
   }
-  block_add_err(e, err);
+  block_add_err(e, a.err);
 }
 
-// rows with BLK_CAP < in-degree <= HUB_T: one warp per row, 4 gathers per lane in flight, shuffle tree
-__global__ void __launch_bounds__(256) pr_medium_kernel(const uint32_t* __restrict__ rows, uint32_t n_rows,
-                                                        const uint32_t* __restrict__ in_ptr,
-                                                        const uint32_t* __restrict__ in_idx,
-                                                        const uint32_t* __restrict__ out_ptr,
-                                                        const uint32_t* __restrict__ slot, float base,
-                                                        float damping, const float* __restrict__ contrib_old,
-                                                        float* __restrict__ contrib_new, float* __restrict__ scores,
-                                                        double* err) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t w = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const uint64_t keep = l2_policy_evict_last();
-  const uint64_t stream = l2_policy_evict_first();
-  double e = 0.0;
-  if (w < n_rows) {
-    const uint32_t r = rows[w];
-    const uint32_t b = in_ptr[r], en = in_ptr[r + 1];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    uint32_t k = b + lane;
-    for (; k + 96 < en; k += 128) {
-      uint32_t i0 = ldg_u32_hint(in_idx + k, stream), i1 = ldg_u32_hint(in_idx + k + 32, stream);
-      uint32_t i2 = ldg_u32_hint(in_idx + k + 64, stream), i3 = ldg_u32_hint(in_idx + k + 96, stream);
-      s0 += ldg_f32_hint(contrib_old + i0, keep);
-      s1 += ldg_f32_hint(contrib_old + i1, keep);
-      s2 += ldg_f32_hint(contrib_old + i2, keep);
-      s3 += ldg_f32_hint(contrib_old + i3, keep);
-    }
-    for (; k < en; k += 32) s0 += ldg_f32_hint(contrib_old + ldg_u32_hint(in_idx + k, stream), keep);
-    const float s = warp_sum((s0 + s1) + (s2 + s3));
-    if (lane == 0) {
-      const float nw = base + damping * s;
-      e = (double)fabsf(nw - scores[r]);
-      scores[r] = nw;
-      const uint32_t od = out_ptr[r + 1] - out_ptr[r];
-      contrib_new[slot[r]] = od ? nw / (float)od : 0.f;
-    }
-  }
-  block_add_err(e, err);
-}
-
-// Hub rows (in-degree > HUB_T): one CTA per chunk of <= HUB_CHUNK in-edges writes a partial sum
-// (fixed tree => deterministic), then one thread per hub row adds its partials in chunk order.
-__global__ void __launch_bounds__(256) pr_hub_partial_kernel(const uint32_t* __restrict__ chunk_beg,
-                                                             const uint32_t* __restrict__ chunk_end,
-                                                             const uint32_t* __restrict__ in_idx,
-                                                             const float* __restrict__ contrib_old,
-                                                             float* __restrict__ partial) {
-  __shared__ float sh[8];
-  const uint64_t keep = l2_policy_evict_last();
-  const uint64_t stream = l2_policy_evict_first();
-  const uint32_t b = chunk_beg[blockIdx.x], en = chunk_end[blockIdx.x];
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  uint32_t k = b + threadIdx.x;
-  for (; k + 768 < en; k += 1024) {
-    uint32_t i0 = ldg_u32_hint(in_idx + k, stream), i1 = ldg_u32_hint(in_idx + k + 256, stream);
-    uint32_t i2 = ldg_u32_hint(in_idx + k + 512, stream), i3 = ldg_u32_hint(in_idx + k + 768, stream);
-    s0 += ldg_f32_hint(contrib_old + i0, keep);
-    s1 += ldg_f32_hint(contrib_old + i1, keep);
-    s2 += ldg_f32_hint(contrib_old + i2, keep);
-    s3 += ldg_f32_hint(contrib_old + i3, keep);
-  }
-  for (; k < en; k += 256) s0 += ldg_f32_hint(contrib_old + ldg_u32_hint(in_idx + k, stream), keep);
-  float s = warp_sum((s0 + s1) + (s2 + s3));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) sh[warp] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float v = 0.f;
-    for (int i = 0; i < 8; ++i) v += sh[i];
-    partial[blockIdx.x] = v;
-  }
-}
-
+// one thread per hub row adds its chunk partials in chunk order (deterministic)
 __global__ void __launch_bounds__(256) pr_hub_final_kernel(const uint32_t* __restrict__ hubs, uint32_t n_hubs,
                                                            const uint32_t* __restrict__ hub_chunk_ptr,
                                                            const float* __restrict__ partial,
-                                                           const uint32_t* __restrict__ out_ptr,
-                                                           const uint32_t* __restrict__ slot, float base,
-                                                           float damping, float* __restrict__ contrib_new,
+                                                           const uint32_t* __restrict__ od, float base, float damping,
+                                                           float* __restrict__ contrib_new,
                                                            float* __restrict__ scores, double* err) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0;
@@ -296,8 +315,8 @@ __global__ void __launch_bounds__(256) pr_hub_final_kernel(const uint32_t* __res
     const float nw = base + damping * s;
     e = (double)fabsf(nw - scores[u]);
     scores[u] = nw;
-    const uint32_t od = out_ptr[u + 1] - out_ptr[u];
-    contrib_new[slot[u]] = od ? nw / (float)od : 0.f;
+    const uint32_t d = od[u];
+    contrib_new[u] = d ? nw / (float)d : 0.f;
   }
   block_add_err(e, err);
 }
@@ -647,7 +666,7 @@ extern "C" void cozo_gpu_graph_free(cozo_gpu_graph_t* g) {
   if (!g) return;
   void* ptrs[] = {g->out_ptr,  g->out_idx,       g->in_ptr,    g->in_idx,   g->out_w,
                   g->hubs,     g->blk_start,     g->hub_chunk_ptr, g->chunk_beg, g->chunk_end,
-                  g->med_rows, g->slot,         g->in_idx_hot};
+                  g->med_rows, g->slot,         g->pr_in_ptr, g->pr_in_idx, g->pr_od};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete g;
@@ -752,30 +771,59 @@ extern "C" int cozo_gpu_graph_stage(cozo_gpu_graph_t** out, uint32_t n, uint64_t
     G_CUDA(cudaDeviceSynchronize());
   }
   if (n) {
-    // hot-first slots for PageRank's contribution vector
-    DevBuf key, key2, val, perm, tmp2;
-    G_CUDA(cudaMalloc(&key.p, (size_t)n * 4));
-    G_CUDA(cudaMalloc(&key2.p, (size_t)n * 4));
-    G_CUDA(cudaMalloc(&val.p, (size_t)n * 4));
-    G_CUDA(cudaMalloc(&perm.p, (size_t)n * 4));
-    G_CUDA(cudaMalloc(&g->slot, (size_t)n * 4));
-    G_CUDA(cudaMalloc(&g->in_idx_hot, mm * 4));
-    pr_degkey_kernel<<<(n + 255) / 256, 256>>>(g->out_ptr, n, key.as<uint32_t>(), val.as<uint32_t>());
-    size_t sb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sb, key.as<uint32_t>(), key2.as<uint32_t>(), val.as<uint32_t>(),
-                                    perm.as<uint32_t>(), (int)n);
-    G_CUDA(cudaMalloc(&tmp2.p, sb));
-    cub::DeviceRadixSort::SortPairs(tmp2.p, sb, key.as<uint32_t>(), key2.as<uint32_t>(), val.as<uint32_t>(),
-                                    perm.as<uint32_t>(), (int)n);
-    pr_slot_kernel<<<(n + 255) / 256, 256>>>(perm.as<uint32_t>(), n, g->slot);
-    if (m)
-      pr_relabel_kernel<<<(uint32_t)((m + 255) / 256), 256>>>(g->in_idx, g->slot, m, g->in_idx_hot);
-    G_CUDA(cudaGetLastError());
-    G_CUDA(cudaDeviceSynchronize());
+    // slot space for PageRank: slot = rank by out-degree (descending); in-CSR relabelled and re-sorted
+    {
+      DevBuf key, key2, val, perm, tmp2;
+      G_CUDA(cudaMalloc(&key.p, (size_t)n * 4));
+      G_CUDA(cudaMalloc(&key2.p, (size_t)n * 4));
+      G_CUDA(cudaMalloc(&val.p, (size_t)n * 4));
+      G_CUDA(cudaMalloc(&perm.p, (size_t)n * 4));
+      G_CUDA(cudaMalloc(&g->slot, (size_t)n * 4));
+      G_CUDA(cudaMalloc(&g->pr_od, (size_t)n * 4));
+      G_CUDA(cudaMalloc(&g->pr_in_ptr, np1 * 4));
+      G_CUDA(cudaMalloc(&g->pr_in_idx, mm * 4));
+      pr_degkey_kernel<<<(n + 255) / 256, 256>>>(g->out_ptr, n, key.as<uint32_t>(), val.as<uint32_t>());
+      size_t sb = 0, sb2 = 0, sb3 = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, sb, key.as<uint32_t>(), key2.as<uint32_t>(), val.as<uint32_t>(),
+                                      perm.as<uint32_t>(), (int)n);
+      cub::DeviceScan::ExclusiveSum(nullptr, sb2, g->pr_in_ptr, g->pr_in_ptr, (int)np1);
+      int end_bit = 32;
+      while (end_bit < 64 && (n >> (end_bit - 32)) != 0) ++end_bit;
+      if (m)
+        cub::DeviceRadixSort::SortKeys(nullptr, sb3, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)m, 0,
+                                       end_bit);
+      sb = std::max(sb, std::max(sb2, sb3));
+      G_CUDA(cudaMalloc(&tmp2.p, sb));
+      {
+        size_t t = sb;
+        cub::DeviceRadixSort::SortPairs(tmp2.p, t, key.as<uint32_t>(), key2.as<uint32_t>(), val.as<uint32_t>(),
+                                        perm.as<uint32_t>(), (int)n);
+      }
+      pr_slot_kernel<<<(n + 255) / 256, 256>>>(perm.as<uint32_t>(), n, g->slot);
+      G_CUDA(cudaMemset(g->pr_in_ptr, 0, np1 * 4));
+      pr_degrees_kernel<<<(n + 255) / 256, 256>>>(g->out_ptr, g->in_ptr, g->slot, n, g->pr_od, g->pr_in_ptr);
+      {
+        size_t t = sb;
+        cub::DeviceScan::ExclusiveSum(tmp2.p, t, g->pr_in_ptr, g->pr_in_ptr, (int)np1);
+      }
+      if (m) {
+        DevBuf k1, k2;
+        G_CUDA(cudaMalloc(&k1.p, m * 8));
+        G_CUDA(cudaMalloc(&k2.p, m * 8));
+        pr_edge_keys_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256>>>(g->in_ptr, g->in_idx, g->slot, n,
+                                                                                 k1.as<unsigned long long>());
+        size_t t = sb;
+        cub::DeviceRadixSort::SortKeys(tmp2.p, t, k1.as<unsigned long long>(), k2.as<unsigned long long>(), (int)m, 0,
+                                       end_bit);
+        split_keys_kernel<<<(uint32_t)((m + 255) / 256), 256>>>(k2.as<unsigned long long>(), m, g->pr_in_idx);
+      }
+      G_CUDA(cudaGetLastError());
+      G_CUDA(cudaDeviceSynchronize());
+    }
     // row blocks for the pull kernel: consecutive rows, <= BLK_CAP in-edges and <= BLK_ROWS rows,
     // hub rows (in-degree > HUB_T) excluded and listed separately
     std::vector<uint32_t> hin(np1);
-    G_CUDA(cudaMemcpy(hin.data(), g->in_ptr, np1 * 4, cudaMemcpyDeviceToHost));
+    G_CUDA(cudaMemcpy(hin.data(), g->pr_in_ptr, np1 * 4, cudaMemcpyDeviceToHost));  // slot-space rows
     std::vector<uint32_t> blocks, hubs, med;
     uint32_t r = 0;
     while (r < n) {
@@ -799,7 +847,7 @@ extern "C" int cozo_gpu_graph_stage(cozo_gpu_graph_t** out, uint32_t n, uint64_t
     // blocks are [r0,r1) pairs; store starts and ends interleaved as consecutive pairs
     g->n_blk = (uint32_t)(blocks.size() / 2);
     g->n_hubs = (uint32_t)hubs.size();
-    // pack as start array with explicit end: pr_iter_kernel reads blk_start[blk], blk_start[blk+1];
+    // pr_pull_kernel reads blk_start[2*blk], blk_start[2*blk+1];
     // gaps (hub rows) make blocks non-contiguous, so keep pairs in a 2*n_blk array
     G_CUDA(cudaMalloc(&g->blk_start, std::max<size_t>(blocks.size(), 2) * 4));
     if (!blocks.empty())
@@ -854,43 +902,62 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   const uint32_t n = g->n;
   if (n == 0) return 0;  // pagerank.rs:43-45
   const DeviceInfo& di = device_info();
-  DevBuf scores, c0, c1, err, partial;
+  DevBuf scores, c0, c1, err, partial, unperm;
   COZO_CUDA(cudaMalloc(&partial.p, (size_t)std::max(g->n_chunks, 1u) * 4));
   COZO_CUDA(cudaMalloc(&scores.p, (size_t)n * 4));
   COZO_CUDA(cudaMalloc(&c0.p, (size_t)n * 4));
   COZO_CUDA(cudaMalloc(&c1.p, (size_t)n * 4));
-  COZO_CUDA(cudaMalloc(&err.p, 8));
+  COZO_CUDA(cudaMalloc(&unperm.p, (size_t)n * 4));
+  COZO_CUDA(cudaMalloc(&err.p, 32));  // f64 error + three u32 work counters
+  PrArgs a{};
+  a.in_ptr = g->pr_in_ptr;
+  a.in_idx = g->pr_in_idx;
+  a.od = g->pr_od;
+  a.blk_start = g->blk_start;
+  a.med_rows = g->med_rows;
+  a.chunk_beg = g->chunk_beg;
+  a.chunk_end = g->chunk_end;
+  a.n_blk = g->n_blk;
+  a.n_med = g->n_med;
+  a.n_chunks = g->n_chunks;
+  a.scores = scores.as<float>();
+  a.partial = partial.as<float>();
+  a.err = err.as<double>();
+  // launch shape: `pagerank.warps` warps per CTA (8 or 32), `pagerank.ctas_per_sm` resident CTAs per SM,
+  // `pagerank.dynamic` = draw work from device counters instead of static round-robin
+  const int64_t warps = get_option("pagerank.warps", 32);
+  const int64_t cps = std::max<int64_t>(1, get_option("pagerank.ctas_per_sm", warps == 32 ? 2 : 8));
+  a.dynamic = get_option("pagerank.dynamic", 1) ? 1u : 0u;
+  const uint64_t items = (uint64_t)g->n_blk + g->n_med + g->n_chunks;
+  const uint32_t wpc = warps == 32 ? 32u : 8u;
+  const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((items + wpc - 1) / wpc, (uint64_t)di.sm_count * (uint64_t)cps));
   cudaEvent_t e0, e1;
   COZO_CUDA(cudaEventCreate(&e0));
   COZO_CUDA(cudaEventCreate(&e1));
   const float init = 1.0f / (float)n;
-  const float base = (1.0f - damping) / (float)n;
+  a.base = (1.0f - damping) / (float)n;
+  a.damping = damping;
   COZO_CUDA(cudaEventRecord(e0));
-  pr_init_kernel<<<(n + 255) / 256, 256>>>(g->out_ptr, g->slot, n, init, scores.as<float>(), c0.as<float>());
+  pr_init_kernel<<<(n + 255) / 256, 256>>>(g->pr_od, n, init, scores.as<float>(), c0.as<float>());
   float* cold = c0.as<float>();
   float* cnew = c1.as<float>();
   uint32_t iter = 0;
   double herr = 0;
-  const uint32_t grid = std::max(1u, std::min<uint32_t>((g->n_blk + 7) / 8, (uint32_t)di.sm_count * 8 * 4));
   int ret = 0;
   for (;;) {
     if (poisoned(poison)) {
       ret = set_error(COZO_GPU_EKILLED, "Running query is killed before completion");
       break;
     }
-    cudaMemsetAsync(err.p, 0, 8);
-    if (g->n_blk)
-      pr_iter_kernel<<<grid, 256>>>(g->blk_start, g->n_blk, g->in_ptr, g->in_idx_hot, g->out_ptr, g->slot, base, damping, cold,
-                                    cnew, scores.as<float>(), err.as<double>());
-    if (g->n_med)
-      pr_medium_kernel<<<(g->n_med + 7) / 8, 256>>>(g->med_rows, g->n_med, g->in_ptr, g->in_idx_hot, g->out_ptr, g->slot, base,
-                                                     damping, cold, cnew, scores.as<float>(), err.as<double>());
-    if (g->n_hubs) {
-      pr_hub_partial_kernel<<<g->n_chunks, 256>>>(g->chunk_beg, g->chunk_end, g->in_idx_hot, cold, partial.as<float>());
+    cudaMemsetAsync(err.p, 0, 32);
+    a.contrib_old = cold;
+    a.contrib_new = cnew;
+    if (wpc == 32) pr_pull_kernel<32, 2><<<grid, 1024>>>(a);
+    else pr_pull_kernel<8, 8><<<grid, 256>>>(a);
+    if (g->n_hubs)
       pr_hub_final_kernel<<<(g->n_hubs + 255) / 256, 256>>>(g->hubs, g->n_hubs, g->hub_chunk_ptr, partial.as<float>(),
-                                                            g->out_ptr, g->slot, base, damping, cnew,
-                                                            scores.as<float>(), err.as<double>());
-    }
+                                                            g->pr_od, a.base, damping, cnew, scores.as<float>(),
+                                                            err.as<double>());
     cudaError_t ce = cudaMemcpy(&herr, err.p, 8, cudaMemcpyDeviceToHost);
     if (ce != cudaSuccess) {
       ret = set_error(COZO_GPU_ECUDA, "pagerank iteration failed: %s", cudaGetErrorString(ce));
@@ -900,6 +967,7 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
     ++iter;
     if (herr < tol || iter == max_iter) break;
   }
+  if (!ret) pr_unpermute_kernel<<<(n + 255) / 256, 256>>>(scores.as<float>(), g->slot, n, unperm.as<float>());
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms = 0;
@@ -907,7 +975,7 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (ret) return ret;
-  COZO_CUDA(cudaMemcpy(out_scores, scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  COZO_CUDA(cudaMemcpy(out_scores, unperm.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   if (out_iters) *out_iters = iter;
   if (out_err) *out_err = herr;
   if (out_kernel_ms) *out_kernel_ms = ms;

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep", default="", help="';'-separated option sets, each 'name=value,name=value'")
     a = ap.parse_args()
     from cozo_b200 import capi
     capi.init(0)
@@ -58,6 +59,14 @@ def main():
            "achieved_GBs": bytes_iter / (best / a.iters / 1e3) / 1e9,
            "frac_of_measured_hbm": bytes_iter / (best / a.iters / 1e3) / 1e9 / 6574.5,
            "defaults_run": {"iters": it_def, "err": err_def, "ms": ms_def}, "gen_s": gen_s, "stage_s": stage_s}
+    if a.sweep:
+        sweep = {}
+        for cfg in a.sweep.split(";"):
+            for kv in cfg.split(","):
+                k, v = kv.split("=")
+                capi.set_option(k, int(v))
+            sweep[cfg] = min(g.pagerank(0.85, 0.0, a.iters)[3] for _ in range(3)) / a.iters
+        out["ms_per_iter_by_options"] = sweep
     if not a.no_cpu:
         from oracle import oracle as O
         cores = os.cpu_count()
