@@ -16,12 +16,16 @@
  *     id <-> (Tuple key, field, sub-index) table (CompoundKey, hnsw.rs:55) or the
  *     id <-> DataValue table (fixed_rule/mod.rs:144-145).
  *   - there is NO CPU fallback: without a usable sm_100 device init fails.
- *   - search / algorithm calls are thread-safe per handle (each call takes its
- *     own stream + workspace from a pool); stage/free are not concurrent with
- *     calls on the same handle.
- *   - `poison` parameters point at the AtomicBool inside Poison
- *     (runtime/db.rs:1926-1942); it is polled between kernel launches and makes
- *     the call return COZO_GPU_EKILLED, mirroring `poison.check()?`.
+ *   - search calls are re-entrant per handle: each call takes its own stream and
+ *     a workspace from a bounded pool.  Graph algorithm calls are thread-safe per
+ *     handle too (the staged graph is read-only, every call owns its buffers) but
+ *     run on the default stream, i.e. concurrent calls serialise on the device.
+ *     stage / free / build / insert / update / remove are not concurrent with
+ *     any other call on the same handle.
+ *   - `poison` parameters point at a 32-bit flag mirroring the AtomicBool inside
+ *     Poison (runtime/db.rs:1926-1942; INTEGRATION.md shows the mirror); it is
+ *     polled between kernel launches and makes the call return COZO_GPU_EKILLED,
+ *     mirroring `poison.check()?`.
  */
 #ifndef COZO_GPU_H
 #define COZO_GPU_H
