@@ -10,7 +10,6 @@
 
 #include <algorithm>
 #include <cmath>
-#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -40,20 +39,6 @@ struct cozo_gpu_graph {
   // hub rows are cut into chunks of <= HUB_CHUNK in-edges, one warp per chunk
   uint32_t *hub_chunk_ptr = nullptr, *chunk_beg = nullptr, *chunk_end = nullptr;
   uint32_t n_chunks = 0;
-  // ---- scatter-then-stream PageRank ("propagation blocking"; built lazily by pb_prepare) ---------
-  // Destination rows are cut into bins (<= PB_W rows, about PB edges each), source-major edges into
-  // PB_G groups of equal size.  `pb_vals` holds one f32 per edge ordered by (bin, group, dst, src):
-  // pass A walks the edges source-major and stores contrib[src] at pb_pos (the stores of one group
-  // fall into a window of m/PB_G values that L2 write-combines); pass B streams a bin's values and
-  // adds them into shared-memory row accumulators through the 16-bit row index pb_dl.
-  std::mutex pb_mu;
-  bool pb_ready = false;
-  uint32_t pb_nb = 0;                                   // bins
-  uint32_t *pb_bin_row = nullptr;                       // [nb+1] first slot-space row of each bin
-  uint32_t *pb_slice_off = nullptr;                     // [nb*PB_G+1] start of slice (bin, group) in pb_vals
-  uint32_t *pb_src = nullptr, *pb_pos = nullptr;        // [m] source-major: source slot, position in pb_vals
-  uint16_t *pb_dl = nullptr;                            // [m] row index inside the bin, pb_vals order
-  float *pb_vals = nullptr;                             // [m]
 };
 
 namespace cozo {
@@ -62,9 +47,6 @@ constexpr uint32_t HUB_T = 4096;   // rows longer than this are cut into HUB_CHU
 constexpr uint32_t BLK_CAP = 256;  // in-edges of a warp's mini-block (8 gathers per lane in flight)
 constexpr uint32_t BLK_ROWS = 32;  // rows per mini-block: one lane sums one row
 constexpr uint32_t HUB_CHUNK = 4096; // in-edges of a hub row summed by one warp
-constexpr uint32_t PB_W = 16384;     // rows per bin at most: 64 KB of shared-memory accumulators
-constexpr uint32_t PB_G = 32;        // source-major groups: the scatter window is m/PB_G values
-constexpr uint32_t PB_WARPS = 16;    // pass B: 512-thread CTAs, 3 per SM
 
 __global__ void edge_check_kernel(const uint32_t* src, const uint32_t* dst, const float* w, uint64_t m, uint32_t n,
                                   int* bad) {
@@ -313,185 +295,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pr_pull_kernel(const PrArgs 
       __syncwarp();
     }
     c.cur += c.stride;
-  }
-  block_add_err(e, a.err);
-}
-
-// ---- scatter-then-stream variant (see struct cozo_gpu_graph) -----------------------------------------
-// staging helpers
-__global__ void pb_row_bin_kernel(const uint32_t* __restrict__ bin_row, uint32_t nb, uint32_t* row_bin) {
-  const uint32_t b = blockIdx.x;
-  if (b >= nb) return;
-  for (uint32_t r = bin_row[b] + threadIdx.x; r < bin_row[b + 1]; r += blockDim.x) row_bin[r] = b;
-}
-// one warp per slot-space destination row: dst row of every in-edge + the source-major sort key
-__global__ void pb_expand_kernel(const uint32_t* __restrict__ in_ptr, const uint32_t* __restrict__ in_idx, uint32_t n,
-                                 uint32_t* dstrow, unsigned long long* key_sm, uint32_t* eid) {
-  const uint32_t w = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= n) return;
-  for (uint32_t e = in_ptr[w] + lane; e < in_ptr[w + 1]; e += 32) {
-    dstrow[e] = w;
-    key_sm[e] = ((unsigned long long)in_idx[e] << 32) | w;
-    eid[e] = e;
-  }
-}
-// i = source-major rank of in-CSR edge perm[i]: record the source, and the (bin, group) key of that edge
-__global__ void pb_group_kernel(const unsigned long long* __restrict__ key_sorted, const uint32_t* __restrict__ perm,
-                                const uint32_t* __restrict__ row_bin, uint64_t m, uint32_t group_edges, uint32_t* src,
-                                uint32_t* key3) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const unsigned long long k = key_sorted[i];
-  src[i] = (uint32_t)(k >> 32);
-  key3[perm[i]] = row_bin[(uint32_t)k] * PB_G + (uint32_t)(i / group_edges);
-}
-__global__ void pb_hist_kernel(const uint32_t* __restrict__ key3, uint64_t m, uint32_t* hist) {
-  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < m) atomicAdd(&hist[key3[e]], 1u);
-}
-// p = rank of in-CSR edge sorted_e[p] in (bin, group, dst, src) order
-__global__ void pb_place_kernel(const uint32_t* __restrict__ sorted_e, const uint32_t* __restrict__ dstrow,
-                                const uint32_t* __restrict__ row_bin, const uint32_t* __restrict__ bin_row, uint64_t m,
-                                uint32_t* pos_of_edge, uint16_t* dl) {
-  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= m) return;
-  const uint32_t e = sorted_e[p];
-  pos_of_edge[e] = (uint32_t)p;
-  const uint32_t r = dstrow[e];
-  dl[p] = (uint16_t)(r - bin_row[row_bin[r]]);
-}
-__global__ void pb_gather_pos_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ pos_of_edge, uint64_t m,
-                                     uint32_t* pos_sm) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) pos_sm[i] = pos_of_edge[perm[i]];
-}
-
-// pass A: vals[pos[i]] = contrib[src[i]] over the source-major edges, four per thread.  The grid walks
-// the edge list front to back, so at any moment all CTAs store into the window of one or two groups.
-__global__ void __launch_bounds__(256) pb_scatter_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ pos,
-                                                         const float* __restrict__ contrib, float* __restrict__ vals,
-                                                         uint64_t m) {
-  const uint64_t stream = l2_policy_evict_first();
-  const uint64_t step = (uint64_t)gridDim.x * blockDim.x * 4;
-  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; base < m; base += step) {
-    uint32_t u[4], p[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint64_t i = base + (uint64_t)j * blockDim.x;
-      u[j] = i < m ? ldg_u32_hint(src + i, stream) : NONE;
-      p[j] = i < m ? ldg_u32_hint(pos + i, stream) : 0u;
-    }
-    float c[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = u[j] != NONE ? __ldg(contrib + u[j]) : 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (u[j] != NONE) vals[p[j]] = c[j];
-  }
-}
-
-struct PbArgs {
-  const uint32_t *bin_row, *slice_off, *od;
-  const uint16_t* dl;
-  const float* vals;
-  uint32_t nb;
-  float base, damping;
-  float *contrib_new, *scores;
-  double* err;  // err[0]; the bin counter is the u32 at err + 1
-};
-
-// pass B: one CTA per bin (drawn from a device counter).  The bin's values arrive as PB_G slices, each
-// sorted by (dst, src).  Per slice the warps take equal ranges; a warp walks its range 32 values at a
-// time (four steps of loads in flight), reduces runs of equal row index with a fixed shuffle tree and
-// the run head adds to the row's accumulator.  A row can straddle a range boundary: the part that
-// CONTINUES a row from the previous warp's range is not added directly but parked per warp and added by
-// one thread, in warp order, after a block barrier - so every accumulator has one writer at a time and
-// the summation order is fixed: the result is deterministic.
-__global__ void __launch_bounds__(PB_WARPS * 32, 3) pb_accumulate_kernel(const PbArgs a) {
-  extern __shared__ float acc[];  // PB_W accumulators (64 KB: above the static limit, hence dynamic)
-  __shared__ uint32_t bdst[PB_WARPS];
-  __shared__ float bsum[PB_WARPS];
-  __shared__ uint32_t cur_bin;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t stream = l2_policy_evict_first();
-  uint32_t* ctr = reinterpret_cast<uint32_t*>(a.err + 1);
-  double e = 0.0;
-  for (;;) {
-    if (threadIdx.x == 0) cur_bin = atomicAdd(ctr, 1u);
-    __syncthreads();
-    const uint32_t b = cur_bin;
-    if (b >= a.nb) break;
-    const uint32_t r0 = a.bin_row[b], nrows = a.bin_row[b + 1] - r0;
-    for (uint32_t i = threadIdx.x; i < nrows; i += PB_WARPS * 32) acc[i] = 0.f;
-    __syncthreads();
-    for (uint32_t g = 0; g < PB_G; ++g) {
-      const uint32_t s0 = a.slice_off[b * PB_G + g], s1 = a.slice_off[b * PB_G + g + 1];
-      if (s0 == s1) continue;  // uniform across the CTA
-      const uint32_t len = s1 - s0;
-      const uint32_t L = (((len + PB_WARPS - 1) / PB_WARPS) + 31u) & ~31u;
-      const uint32_t start = min(s0 + (uint32_t)warp * L, s1), end = min(start + L, s1);
-      uint32_t dfirst = NONE;
-      bool first_active = false;  // still inside a run that continues the previous warp's last row
-      if (warp > 0 && start < end) {
-        dfirst = a.dl[start];
-        first_active = (uint32_t)a.dl[start - 1] == dfirst;
-      }
-      const bool defer = first_active;
-      float fsum = 0.f;
-      for (uint32_t j = start; j < end; j += 128) {
-        float v4[4];
-        uint32_t d4[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint32_t idx = j + 32 * t + lane;
-          const bool valid = idx < end;
-          v4[t] = valid ? ldg_f32_hint(a.vals + idx, stream) : 0.f;
-          d4[t] = valid ? (uint32_t)a.dl[idx] : 0x10000u + (uint32_t)lane;  // invalid lanes: singleton runs
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (j + 32 * t >= end) break;  // uniform
-          float v = v4[t];
-          const uint32_t d = d4[t];
-          const bool valid = d < 0x10000u;
-          const uint32_t dprev = __shfl_up_sync(0xffffffffu, d, 1);
-          const bool head = lane == 0 || d != dprev;
-          const uint32_t heads = __ballot_sync(0xffffffffu, head);
-          const uint32_t above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);  // heads in lanes > lane
-          const int last = above ? __ffs(above) - 2 : 31;                            // last lane of my run
-#pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            const float tv = __shfl_down_sync(0xffffffffu, v, off);
-            if (lane + off <= last) v += tv;
-          }
-          if (head && valid) {
-            if (first_active && lane == 0 && d == dfirst) fsum += v;
-            else acc[d] += v;
-          }
-          if (first_active && __ballot_sync(0xffffffffu, valid && d != dfirst)) first_active = false;
-          __syncwarp();
-        }
-      }
-      if (lane == 0) {
-        bdst[warp] = defer ? dfirst : NONE;
-        bsum[warp] = fsum;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0)
-        for (int w = 1; w < (int)PB_WARPS; ++w)
-          if (bdst[w] != NONE) acc[bdst[w]] += bsum[w];
-      __syncthreads();
-    }
-    for (uint32_t i = threadIdx.x; i < nrows; i += PB_WARPS * 32) {
-      const uint32_t r = r0 + i;
-      const float nw = a.base + a.damping * acc[i];
-      e += (double)fabsf(nw - a.scores[r]);
-      a.scores[r] = nw;
-      const uint32_t od = a.od[r];
-      a.contrib_new[r] = od ? nw / (float)od : 0.f;
-    }
-    __syncthreads();
   }
   block_add_err(e, a.err);
 }
@@ -863,8 +666,7 @@ extern "C" void cozo_gpu_graph_free(cozo_gpu_graph_t* g) {
   if (!g) return;
   void* ptrs[] = {g->out_ptr,  g->out_idx,       g->in_ptr,    g->in_idx,   g->out_w,
                   g->hubs,     g->blk_start,     g->hub_chunk_ptr, g->chunk_beg, g->chunk_end,
-                  g->med_rows, g->slot,         g->pr_in_ptr, g->pr_in_idx, g->pr_od,
-                  g->pb_bin_row, g->pb_slice_off, g->pb_src,   g->pb_pos,    g->pb_dl,  g->pb_vals};
+                  g->med_rows, g->slot,         g->pr_in_ptr, g->pr_in_idx, g->pr_od};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete g;
@@ -1087,91 +889,6 @@ extern "C" int cozo_gpu_graph_export(cozo_gpu_graph_t* g, uint32_t* out_ptr, uin
   return 0;
 }
 
-// Build the scatter-then-stream structures of a staged graph (once per handle, on first use).
-static int pb_prepare(cozo_gpu_graph_t* g) {
-  std::lock_guard<std::mutex> lk(g->pb_mu);
-  if (g->pb_ready) return 0;
-  const uint32_t n = g->n;
-  const uint64_t m = g->m;
-  if (m == 0 || m >= 0xFFFFFFFFull) return set_error(COZO_GPU_EUNSUP, "scatter-then-stream PageRank needs 0 < m < 2^32");
-  const size_t np1 = (size_t)n + 1;
-  // bins: consecutive slot-space rows, <= PB_W rows and about e_bin in-edges (a longer row is a bin of its own)
-  std::vector<uint32_t> hin(np1);
-  COZO_CUDA(cudaMemcpy(hin.data(), g->pr_in_ptr, np1 * 4, cudaMemcpyDeviceToHost));
-  const uint32_t e_bin = (uint32_t)std::max<uint64_t>(65536, m / 1024);
-  std::vector<uint32_t> bin_row(1, 0);
-  for (uint32_t r = 0; r < n;) {
-    const uint32_t r0 = r;
-    ++r;
-    while (r < n && r - r0 < PB_W && hin[r + 1] - hin[r0] <= e_bin) ++r;
-    bin_row.push_back(r);
-  }
-  const uint32_t nb = (uint32_t)bin_row.size() - 1;
-  const size_t n_slices = (size_t)nb * PB_G;
-  const uint32_t group_edges = (uint32_t)((m + PB_G - 1) / PB_G);
-  DevBuf row_bin, dstrow, k1, k2, e1, e2, key3, key3b, pos_of_edge, tmp;
-  COZO_CUDA(cudaMalloc(&g->pb_bin_row, bin_row.size() * 4));
-  COZO_CUDA(cudaMemcpy(g->pb_bin_row, bin_row.data(), bin_row.size() * 4, cudaMemcpyHostToDevice));
-  COZO_CUDA(cudaMalloc(&g->pb_slice_off, (n_slices + 1) * 4));
-  COZO_CUDA(cudaMalloc(&g->pb_src, m * 4));
-  COZO_CUDA(cudaMalloc(&g->pb_pos, m * 4));
-  COZO_CUDA(cudaMalloc(&g->pb_dl, m * 2));
-  COZO_CUDA(cudaMalloc(&g->pb_vals, m * 4));
-  COZO_CUDA(cudaMalloc(&row_bin.p, (size_t)n * 4));
-  COZO_CUDA(cudaMalloc(&dstrow.p, m * 4));
-  COZO_CUDA(cudaMalloc(&k1.p, m * 8));
-  COZO_CUDA(cudaMalloc(&k2.p, m * 8));
-  COZO_CUDA(cudaMalloc(&e1.p, m * 4));
-  COZO_CUDA(cudaMalloc(&e2.p, m * 4));
-  COZO_CUDA(cudaMalloc(&key3.p, m * 4));
-  COZO_CUDA(cudaMalloc(&key3b.p, m * 4));
-  COZO_CUDA(cudaMalloc(&pos_of_edge.p, m * 4));
-  int end_bit = 32;
-  while (end_bit < 64 && (n >> (end_bit - 32)) != 0) ++end_bit;
-  int key3_bits = 1;
-  while (key3_bits < 32 && (n_slices >> key3_bits) != 0) ++key3_bits;
-  size_t t1 = 0, t2 = 0, t3 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, t1, k1.as<unsigned long long>(), k2.as<unsigned long long>(), e1.as<uint32_t>(),
-                                  e2.as<uint32_t>(), (int)m, 0, end_bit);
-  cub::DeviceRadixSort::SortPairs(nullptr, t2, key3.as<uint32_t>(), key3b.as<uint32_t>(), e1.as<uint32_t>(),
-                                  e2.as<uint32_t>(), (int)m, 0, key3_bits);
-  cub::DeviceScan::ExclusiveSum(nullptr, t3, g->pb_slice_off, g->pb_slice_off, (int)(n_slices + 1));
-  const size_t tmp_bytes = std::max(t1, std::max(t2, t3));
-  COZO_CUDA(cudaMalloc(&tmp.p, tmp_bytes));
-  const uint32_t gb = (uint32_t)((m + 255) / 256);
-  pb_row_bin_kernel<<<nb, 256>>>(g->pb_bin_row, nb, row_bin.as<uint32_t>());
-  pb_expand_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256>>>(g->pr_in_ptr, g->pr_in_idx, n, dstrow.as<uint32_t>(),
-                                                                        k1.as<unsigned long long>(), e1.as<uint32_t>());
-  {  // source-major order of the in-CSR edges: sort by (src, dst); e2[i] = in-CSR index of the i-th source-major edge
-    size_t t = tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(tmp.p, t, k1.as<unsigned long long>(), k2.as<unsigned long long>(), e1.as<uint32_t>(),
-                                    e2.as<uint32_t>(), (int)m, 0, end_bit);
-  }
-  pb_group_kernel<<<gb, 256>>>(k2.as<unsigned long long>(), e2.as<uint32_t>(), row_bin.as<uint32_t>(), m, group_edges,
-                               g->pb_src, key3.as<uint32_t>());
-  COZO_CUDA(cudaMemset(g->pb_slice_off, 0, (n_slices + 1) * 4));
-  pb_hist_kernel<<<gb, 256>>>(key3.as<uint32_t>(), m, g->pb_slice_off);
-  {
-    size_t t = tmp_bytes;
-    cub::DeviceScan::ExclusiveSum(tmp.p, t, g->pb_slice_off, g->pb_slice_off, (int)(n_slices + 1));
-  }
-  // (bin, group, dst, src) order: a STABLE sort of the in-CSR edges (already in (dst, src) order) by (bin, group)
-  iota_kernel<<<gb, 256>>>(e1.as<uint32_t>(), m);
-  {
-    size_t t = tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(tmp.p, t, key3.as<uint32_t>(), key3b.as<uint32_t>(), e1.as<uint32_t>(),
-                                    k1.as<uint32_t>(), (int)m, 0, key3_bits);  // k1 reused as the u32 output payload
-  }
-  pb_place_kernel<<<gb, 256>>>(k1.as<uint32_t>(), dstrow.as<uint32_t>(), row_bin.as<uint32_t>(), g->pb_bin_row, m,
-                               pos_of_edge.as<uint32_t>(), g->pb_dl);
-  pb_gather_pos_kernel<<<gb, 256>>>(e2.as<uint32_t>(), pos_of_edge.as<uint32_t>(), m, g->pb_pos);
-  COZO_CUDA(cudaGetLastError());
-  COZO_CUDA(cudaDeviceSynchronize());
-  g->pb_nb = nb;
-  g->pb_ready = true;
-  return 0;
-}
-
 extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol, uint32_t max_iter,
                                  float* out_scores, uint32_t* out_iters, double* out_err, double* out_kernel_ms,
                                  const volatile int* poison) {
@@ -1211,28 +928,6 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   const int64_t warps = get_option("pagerank.warps", 32);
   const int64_t cps = std::max<int64_t>(1, get_option("pagerank.ctas_per_sm", warps == 32 ? 2 : 8));
   a.dynamic = get_option("pagerank.dynamic", 1) ? 1u : 0u;
-  // `pagerank.mode`: 0 = gather pull (pr_pull_kernel), 1 = scatter-then-stream (pb_* kernels), -1 = by size
-  int64_t mode = get_option("pagerank.mode", 0);
-  if (mode < 0) mode = g->m >= (uint64_t)get_option("pagerank.pb_min_edges", 1 << 22) && g->m < 0xFFFFFFFFull ? 1 : 0;
-  if (mode == 1 && g->m == 0) mode = 0;
-  PbArgs pa{};
-  uint32_t pb_grid = 0, sc_grid = 0;
-  const int64_t pb_skip = get_option("pagerank.pb_skip", 0);  // timing aid only: 1 = no pass A, 2 = no pass B (wrong results)
-  if (mode == 1) {
-    rc = pb_prepare(g);
-    if (rc) return rc;
-    pa.bin_row = g->pb_bin_row;
-    pa.slice_off = g->pb_slice_off;
-    pa.od = g->pr_od;
-    pa.dl = g->pb_dl;
-    pa.vals = g->pb_vals;
-    pa.nb = g->pb_nb;
-    pa.scores = scores.as<float>();
-    pa.err = err.as<double>();
-    COZO_CUDA(cudaFuncSetAttribute(pb_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PB_W * 4)));
-    pb_grid = std::max(1u, std::min<uint32_t>(g->pb_nb, (uint32_t)di.sm_count * 3));
-    sc_grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((g->m + 1023) / 1024, (uint64_t)di.sm_count * 8));
-  }
   const uint64_t items = (uint64_t)g->n_blk + g->n_med + g->n_chunks;
   const uint32_t wpc = warps == 32 ? 32u : 8u;
   const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((items + wpc - 1) / wpc, (uint64_t)di.sm_count * (uint64_t)cps));
@@ -1257,15 +952,9 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
     cudaMemsetAsync(err.p, 0, 32);
     a.contrib_old = cold;
     a.contrib_new = cnew;
-    if (mode == 1) {
-      pa.contrib_new = cnew;
-      pa.base = a.base;
-      pa.damping = damping;
-      if (pb_skip != 1) pb_scatter_kernel<<<sc_grid, 256>>>(g->pb_src, g->pb_pos, cold, g->pb_vals, g->m);
-      if (pb_skip != 2) pb_accumulate_kernel<<<pb_grid, PB_WARPS * 32, PB_W * 4>>>(pa);
-    } else if (wpc == 32) pr_pull_kernel<32, 2><<<grid, 1024>>>(a);
+    if (wpc == 32) pr_pull_kernel<32, 2><<<grid, 1024>>>(a);
     else pr_pull_kernel<8, 8><<<grid, 256>>>(a);
-    if (mode != 1 && g->n_hubs)
+    if (g->n_hubs)
       pr_hub_final_kernel<<<(g->n_hubs + 255) / 256, 256>>>(g->hubs, g->n_hubs, g->hub_chunk_ptr, partial.as<float>(),
                                                             g->pr_od, a.base, damping, cnew, scores.as<float>(),
                                                             err.as<double>());

@@ -37,22 +37,14 @@ def test_stage_rejects_bad_edges(gpu):
         gpu.Graph(3, [0, 1], [1, 2], [1.0, np.inf])     # non finite (mod.rs:258-271)
 
 
-@pytest.fixture(params=[0, 1], ids=["gather", "scatter_stream"])
-def pr_mode(gpu, request):
-    """both PageRank implementations (pagerank.mode): 0 = gather pull, 1 = scatter-then-stream"""
-    gpu.set_option("pagerank.mode", request.param)
-    yield request.param
-    gpu.set_option("pagerank.mode", -1)
-
-
 @pytest.mark.parametrize("scale,iters,tol", [(10, 10, 1e-4), (14, 10, 1e-4), (14, 50, 0.0), (12, 3, 0.0), (17, 5, 0.0)])
-def test_pagerank_rmat_parity(gpu, pr_mode, scale, iters, tol):
+def test_pagerank_rmat_parity(gpu, scale, iters, tol):
     n, src, dst = rmat_edges(scale, 16, 0x5EED0004)
     g = gpu.Graph(n, src, dst)
     o = O.OracleGraph(n, src, dst)
     gs, git, gerr, _ = g.pagerank(0.85, tol, iters)
-    if scale == 17 and pr_mode == 1:
-        gs2, _, gerr2, _ = g.pagerank(0.85, tol, iters)     # fixed summation order: bit-identical reruns
+    if scale == 17:
+        gs2, _, _, _ = g.pagerank(0.85, tol, iters)         # work is drawn dynamically, sums are not: bit-identical reruns
         assert np.array_equal(gs, gs2)
     os_, oit, oerr = o.pagerank(0.85, tol, iters, variant="jacobi", n_threads=8)
     assert git == oit
@@ -62,7 +54,7 @@ def test_pagerank_rmat_parity(gpu, pr_mode, scale, iters, tol):
     assert abs(gerr - oerr) <= 0.02 * oerr + 1e-6
 
 
-def test_pagerank_fixed_point_matches_gs_variant(gpu, pr_mode):
+def test_pagerank_fixed_point_matches_gs_variant(gpu):
     """graph 0.3.1 may update contributions in place (Gauss-Seidel); both schedules share the
     fixed point, so converged GPU scores must match the GS oracle too."""
     n, src, dst = rmat_edges(11, 16, 7)
@@ -73,7 +65,7 @@ def test_pagerank_fixed_point_matches_gs_variant(gpu, pr_mode):
     assert np.max(np.abs(gs - os_) / os_) <= 1e-5
 
 
-def test_pagerank_edge_cases(gpu, pr_mode):
+def test_pagerank_edge_cases(gpu):
     g = gpu.Graph(0, np.zeros(0, np.uint32), np.zeros(0, np.uint32))
     s, it, err, _ = g.pagerank()
     assert s.size == 0 and it == 0                          # pagerank.rs:43-45
