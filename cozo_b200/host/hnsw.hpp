@@ -15,6 +15,7 @@
 #include <functional>
 #include <map>
 #include <optional>
+#include <thread>
 
 #include "fixed_rule.hpp"
 #include "memcmp.hpp"
@@ -74,6 +75,11 @@ struct KvRelation {
       r.kv.emplace_back(memcmp_codec::encode_as_key(row.first, id), msgpack_codec::encode_vals(row.second, r.n_keys, id));
     std::sort(r.kv.begin(), r.kv.end());  // byte order == value order, so this is a no-op check in practice
     return r;
+  }
+  const std::string* get_val_bytes(const std::string& k) const {
+    auto it = std::lower_bound(kv.begin(), kv.end(), k,
+                               [](const std::pair<std::string, std::string>& a, const std::string& b) { return a.first < b; });
+    return (it != kv.end() && it->first == k) ? &it->second : nullptr;
   }
   // point read: RelationHandle::get (relation.rs:398-417)
   const std::string* get_val(const Tuple& key) const {
@@ -148,6 +154,18 @@ inline std::string sha256_le_f32(const std::vector<float>& v) {
   return out;
 }
 
+// Everything cozo_gpu_hnsw_stage needs, as plain host arrays: the product of reading `rel:idx` (+ the
+// vectors of `rel`).  Two producers — from decoded tuples (plan_with) and straight from KV bytes
+// (plan_kv_bytes) — must agree element for element; tests/test_stage_plan_cpu.py holds them to that.
+struct StagePlan {
+  std::vector<CompoundKey> keys;  // dense id -> compound key (key order)
+  uint32_t entry = COZO_GPU_NONE, n_levels = 1;
+  std::vector<std::vector<uint32_t>> node_ids, col_idx;  // per level (node_ids[0] stays empty: all nodes)
+  std::vector<std::vector<uint64_t>> row_ptr;
+  std::vector<float> vectors;
+  uint64_t n_edges_kept = 0, n_rows_dropped_same_key = 0, n_rows_dropped_ignored = 0;
+};
+
 // The device-resident copy of one index: a cache of the index relation.
 struct StagedHnswIndex {
   cozo_gpu_hnsw_t* h = nullptr;
@@ -179,19 +197,24 @@ struct StagedHnswIndex {
     });
   }
 
-  // The same, reading both relations from their KV bytes: index keys through the
-  // memcmp codec, `ignore_link` and the vectors through the msgpack value codec, no row materialised
-  // for the base relation (msgpack_codec::extract_vector).
+  // The same from the KV bytes of both relations, without decoding a single index row
+  // into DataValues: see plan_kv_bytes.
   void stage_kv(const KvRelation& base, const KvRelation& idx, const HnswIndexManifest& mf) {
+    upload(plan_kv_bytes(base, idx, mf), mf);
+  }
+
+  // Reference implementation of stage_kv: decode every KV pair into a tuple first (decode_tuple_from_kv),
+  // then plan as `stage` does.  Kept as the cross-check of the byte-level planner.
+  static StagePlan plan_kv_tuples(const KvRelation& base, const KvRelation& idx, const HnswIndexManifest& mf) {
     std::vector<Tuple> idx_rows;
     idx_rows.reserve(idx.kv.size());
     for (auto& kv : idx.kv) idx_rows.push_back(decode_tuple_from_kv(kv.first, kv.second));
     const size_t K = base.n_keys;
-    stage_with(K, std::move(idx_rows), mf, [&](const CompoundKey& ck, float* out) {
+    return plan_with(K, std::move(idx_rows), mf, [&](const CompoundKey& ck, float* out) {
       const std::string* val = base.get_val(std::get<0>(ck));
       if (!val) throw CozoError("", "Cannot find compound key for HNSW");
       const size_t fld = std::get<1>(ck);
-      if (fld < K) {  // a vector stored in a key column: decode it from the compound key itself
+      if (fld < K) {  // a vector stored in a key column: it is part of the compound key itself
         const DataValue& f = std::get<0>(ck)[fld];
         if (f.kind != DataValue::Vec || f.v->size() != mf.vec_dim)
           throw CozoError("", "Cannot interpret " + f.repr() + " as vector");
@@ -202,10 +225,227 @@ struct StagedHnswIndex {
     });
   }
 
+  // Byte-level planner.  An index key is  relid(8) | layer | FROM | TO  where FROM and TO are the memcmp
+  // encodings of (k.., field, sub_idx): self-delimiting, order-preserving and canonical, so
+  //   * the scan order of the relation IS (layer, FROM, TO) order: per level, rows arrive grouped by FROM,
+  //   * dense ids are the ranks of the distinct FROM byte strings of the layer-0 block,
+  //   * a TO is resolved by binary search over those byte strings,
+  //   * "same base row" (hnsw.rs:609) is byte equality of the k.. prefixes,
+  //   * the base row of a vector is found under  base relid | k.. bytes  with no re-encoding.
+  // Only `layer`, `field`, `sub_idx` (integers), `ignore_link` (one msgpack bool) and the n compound keys
+  // handed back for result assembly are ever decoded.
+  static StagePlan plan_kv_bytes(const KvRelation& base, const KvRelation& idx, const HnswIndexManifest& mf) {
+    if (mf.dtype_f64)
+      throw CozoError("gpu::unsupported", "F64 vector indexes are outside the device envelope (f32 only)");
+    using memcmp_codec::skip_datavalue;
+    const size_t K = base.n_keys;
+    struct Row {
+      int64_t layer;
+      const uint8_t *from, *to;  // start of FROM / TO
+      uint32_t from_len, from_klen, to_len, to_klen;
+      bool canary, ignored;
+      const std::string* val;
+    };
+    std::vector<Row> rows(idx.kv.size());
+    auto parse_range = [&](size_t lo, size_t hi) {
+      for (size_t ri = lo; ri < hi; ++ri) {
+        auto& kv = idx.kv[ri];
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(kv.first.data());
+        const uint8_t* end = p + kv.first.size();
+        if (kv.first.size() < memcmp_codec::ENCODED_KEY_MIN_LEN) throw CozoError("", "key shorter than the relation id prefix");
+        p += memcmp_codec::ENCODED_KEY_MIN_LEN;
+        DataValue layer;
+        p += memcmp_codec::decode_datavalue(p, (size_t)(end - p), layer);
+        Row r{};
+        if (!layer.get_int(r.layer)) throw CozoError("", "corrupted index: layer is not an integer");
+        r.val = &kv.second;
+        auto part = [&](const uint8_t*& start, uint32_t& len, uint32_t& klen, bool& null_field) {
+          start = p;
+          for (size_t i = 0; i < K; ++i) p += skip_datavalue(p, (size_t)(end - p));
+          klen = (uint32_t)(p - start);
+          null_field = p < end && *p == memcmp_codec::NULL_TAG;
+          p += skip_datavalue(p, (size_t)(end - p));  // field
+          p += skip_datavalue(p, (size_t)(end - p));  // sub_idx
+          len = (uint32_t)(p - start);
+        };
+        bool to_null = false;
+        part(r.from, r.from_len, r.from_klen, r.canary);  // canary row: fr__field is Null (hnsw.rs:903-909)
+        part(r.to, r.to_len, r.to_klen, to_null);
+        if (p != end) throw CozoError("", "corrupted index: bad row width");
+        // ignore_link is read here, next to the key, while the pair is in cache (hnsw.rs:618-620)
+        r.ignored = r.layer <= 0 && !r.canary && msgpack_codec::read_bool_column(kv.second, 2);
+        rows[ri] = r;
+      }
+    };
+    {  // rows are independent: parse them on a few threads (exceptions are carried back to the caller)
+      const size_t nt = std::max<size_t>(1, std::min<size_t>({(size_t)std::thread::hardware_concurrency(), (size_t)16,
+                                                              rows.size() / 65536 + 1}));
+      std::vector<std::thread> th;
+      std::vector<std::exception_ptr> errs(nt);
+      for (size_t t = 0; t < nt; ++t)
+        th.emplace_back([&, t] {
+          try {
+            parse_range(rows.size() * t / nt, rows.size() * (t + 1) / nt);
+          } catch (...) {
+            errs[t] = std::current_exception();
+          }
+        });
+      for (auto& t : th) t.join();
+      for (auto& e : errs)
+        if (e) std::rethrow_exception(e);
+    }
+    auto key_less = [](const Row& a, const Row& b) {  // (layer, FROM, TO): the storage order
+      if (a.layer != b.layer) return a.layer < b.layer;
+      int c = std::memcmp(a.from, b.from, std::min(a.from_len, b.from_len));
+      if (c || a.from_len != b.from_len) return c ? c < 0 : a.from_len < b.from_len;
+      c = std::memcmp(a.to, b.to, std::min(a.to_len, b.to_len));
+      return c ? c < 0 : a.to_len < b.to_len;
+    };
+    if (!std::is_sorted(rows.begin(), rows.end(), key_less)) std::sort(rows.begin(), rows.end(), key_less);
+    StagePlan pl;
+    // dense ids: distinct FROMs of the layer-0 block, which is contiguous and sorted
+    std::vector<std::pair<const uint8_t*, uint32_t>> froms;
+    for (const Row& r : rows) {
+      if (r.layer != 0 || r.canary) continue;
+      if (froms.empty() || froms.back().second != r.from_len || std::memcmp(froms.back().first, r.from, r.from_len) != 0)
+        froms.emplace_back(r.from, r.from_len);
+    }
+    const uint32_t n = (uint32_t)froms.size();
+    // FROM / TO bytes -> dense id: open addressing over the byte strings (FNV-1a), ids = ranks in `froms`
+    std::vector<uint32_t> table(n ? (size_t)1 << (64 - __builtin_clzll((uint64_t)n * 2)) : 1, COZO_GPU_NONE);
+    const size_t tmask = table.size() - 1;
+    auto hash_of = [](const uint8_t* b, uint32_t len) {
+      uint64_t hsh = 1469598103934665603ull;
+      for (uint32_t i = 0; i < len; ++i) hsh = (hsh ^ b[i]) * 1099511628211ull;
+      return (size_t)(hsh ^ (hsh >> 29));
+    };
+    for (uint32_t i = 0; i < n; ++i) {
+      size_t slot = hash_of(froms[i].first, froms[i].second) & tmask;
+      while (table[slot] != COZO_GPU_NONE) slot = (slot + 1) & tmask;
+      table[slot] = i;
+    }
+    auto id_of = [&](const uint8_t* b, uint32_t len) -> uint32_t {
+      if (n == 0) return COZO_GPU_NONE;
+      for (size_t slot = hash_of(b, len) & tmask;; slot = (slot + 1) & tmask) {
+        const uint32_t i = table[slot];
+        if (i == COZO_GPU_NONE) return COZO_GPU_NONE;
+        if (froms[i].second == len && std::memcmp(froms[i].first, b, len) == 0) return i;
+      }
+    };
+    // the compound keys handed back for result assembly (n decodes, not one per row)
+    pl.keys.reserve(n);
+    for (auto& f : froms) {
+      Tuple t;
+      size_t off = 0;
+      while (off < f.second) {
+        DataValue v;
+        off += memcmp_codec::decode_datavalue(f.first + off, f.second - off, v);
+        t.push_back(std::move(v));
+      }
+      if (t.size() != K + 2) throw CozoError("", "corrupted index: bad row width");
+      int64_t fld = 0, sub = 0;
+      if (!t[K].get_int(fld) || !t[K + 1].get_int(sub)) throw CozoError("", "corrupted index: field / sub index");
+      t.resize(K);
+      pl.keys.emplace_back(std::move(t), (size_t)fld, (int32_t)sub);
+    }
+    // entry point: the first row in key order with layer in [i64::MIN, 1] (hnsw.rs:891-899)
+    int64_t bottom_level = 0;
+    for (const Row& r : rows) {
+      if (r.layer > 1) continue;
+      if (!r.canary) {
+        bottom_level = r.layer;
+        pl.entry = id_of(r.from, r.from_len);
+        if (pl.entry == COZO_GPU_NONE) throw CozoError("", "corrupted index");
+      }
+      break;
+    }
+    pl.n_levels = pl.entry == COZO_GPU_NONE ? 1 : (uint32_t)(-bottom_level) + 1;
+    pl.node_ids.assign(pl.n_levels, {});
+    pl.col_idx.assign(pl.n_levels, {});
+    pl.row_ptr.assign(pl.n_levels, std::vector<uint64_t>(1, 0));
+    // adjacency with the reading rules of hnsw_get_neighbours(include_deleted=false); per level the rows
+    // arrive grouped by FROM in ascending id order, so the CSR is appended to directly
+    std::vector<uint32_t> cur(pl.n_levels, COZO_GPU_NONE);  // the FROM whose row is open, per level
+    uint32_t next0 = 0;                                     // level 0 lists every id: rows closed so far
+    const uint8_t* last_from = nullptr;
+    uint32_t last_len = 0, last_fi = COZO_GPU_NONE;
+    for (const Row& r : rows) {
+      if (r.layer > 0 || r.canary) continue;
+      const uint32_t L = (uint32_t)(-r.layer);
+      if (L >= pl.n_levels) continue;
+      // rows of one FROM are consecutive: resolve it once
+      if (!(last_from && last_len == r.from_len && std::memcmp(last_from, r.from, r.from_len) == 0)) {
+        last_from = r.from;
+        last_len = r.from_len;
+        last_fi = id_of(r.from, r.from_len);
+        if (last_fi == COZO_GPU_NONE) throw CozoError("", "corrupted index");
+      }
+      const uint32_t fi = last_fi;
+      if (cur[L] != fi) {  // open a new row (self-loop rows create the, possibly empty, row)
+        if (L == 0) {
+          for (; next0 < fi; ++next0) pl.row_ptr[0].push_back(pl.col_idx[0].size());  // ids without rows
+          next0 = fi + 1;
+        } else {
+          pl.node_ids[L].push_back(fi);
+        }
+        pl.row_ptr[L].push_back(pl.col_idx[L].size());
+        cur[L] = fi;
+      }
+      if (r.to_klen == r.from_klen && std::memcmp(r.to, r.from, r.from_klen) == 0) {  // hnsw.rs:609: tuple key only
+        pl.n_rows_dropped_same_key++;
+        continue;
+      }
+      if (r.ignored) {  // hnsw.rs:618-620
+        pl.n_rows_dropped_ignored++;
+        continue;
+      }
+      const uint32_t ti = id_of(r.to, r.to_len);
+      if (ti == COZO_GPU_NONE) throw CozoError("", "corrupted index: edge to an unknown vector");
+      pl.col_idx[L].push_back(ti);
+      pl.row_ptr[L].back() = pl.col_idx[L].size();
+      pl.n_edges_kept++;
+    }
+    for (; next0 < n; ++next0) pl.row_ptr[0].push_back(pl.col_idx[0].size());
+    // vectors: VectorCache::ensure_key (hnsw.rs:122-151) against the base relation's KV bytes
+    pl.vectors.resize((size_t)n * mf.vec_dim);
+    std::string bkey;
+    for (uint32_t i = 0; i < n; ++i) {
+      float* out = pl.vectors.data() + (size_t)i * mf.vec_dim;
+      const size_t fld = std::get<1>(pl.keys[i]);
+      if (fld < K) {
+        const DataValue& f = std::get<0>(pl.keys[i])[fld];
+        if (f.kind != DataValue::Vec || f.v->size() != mf.vec_dim)
+          throw CozoError("", "Cannot interpret " + f.repr() + " as vector");
+        std::copy(f.v->begin(), f.v->end(), out);
+        continue;
+      }
+      bkey.clear();
+      memcmp_codec::put_u64_be(bkey, base.id);
+      // the k.. bytes of FROM are the base relation's key bytes: klen = length of the first K values
+      {
+        size_t klen = 0;
+        for (size_t c = 0; c < K; ++c) klen += skip_datavalue(froms[i].first + klen, froms[i].second - klen);
+        bkey.append(reinterpret_cast<const char*>(froms[i].first), klen);
+      }
+      const std::string* val = base.get_val_bytes(bkey);
+      if (!val) throw CozoError("", "Cannot find compound key for HNSW");
+      msgpack_codec::extract_vector(*val, fld - K, std::get<2>(pl.keys[i]), out, mf.vec_dim);
+    }
+    return pl;
+  }
+
   // fetch(compound key, out[vec_dim]) = VectorCache::ensure_key (hnsw.rs:122-151)
   template <class Fetch>
   void stage_with(size_t K, std::vector<Tuple> idx_rows, const HnswIndexManifest& mf, Fetch fetch) {
-    manifest = mf;
+    upload(plan_with(K, std::move(idx_rows), mf, fetch), mf);
+  }
+
+  template <class Fetch>
+  static StagePlan plan_with(size_t K, std::vector<Tuple> idx_rows, const HnswIndexManifest& mf, Fetch fetch) {
+    StagePlan pl;
+    std::vector<CompoundKey>& keys = pl.keys;
+    uint64_t &n_edges_kept = pl.n_edges_kept, &n_rows_dropped_same_key = pl.n_rows_dropped_same_key,
+             &n_rows_dropped_ignored = pl.n_rows_dropped_ignored;
     if (mf.dtype_f64)
       throw CozoError("gpu::unsupported", "F64 vector indexes are outside the device envelope (f32 only)");
     std::sort(idx_rows.begin(), idx_rows.end(), TupleLess());
@@ -233,15 +473,13 @@ struct StagedHnswIndex {
       ids.emplace(f, 0u);
     }
     keys.clear();
-    key_ids.clear();
-    live.clear();
     for (auto& kv : ids) {
       kv.second = (uint32_t)keys.size();
       keys.push_back(kv.first);
     }
     const uint32_t n = (uint32_t)keys.size();
     // entry point: the first row in key order with layer in [i64::MIN, 1] (hnsw.rs:891-899)
-    uint32_t entry = COZO_GPU_NONE;
+    uint32_t& entry = pl.entry;
     int64_t bottom_level = 0;
     for (const Tuple& t : idx_rows) {
       int64_t layer;
@@ -256,9 +494,10 @@ struct StagedHnswIndex {
       }
       break;
     }
-    const uint32_t n_levels = entry == COZO_GPU_NONE ? 1 : (uint32_t)(-bottom_level) + 1;
+    const uint32_t n_levels = pl.n_levels = entry == COZO_GPU_NONE ? 1 : (uint32_t)(-bottom_level) + 1;
     // adjacency with the reading rules of hnsw_get_neighbours(include_deleted=false)
-    std::vector<std::vector<uint32_t>> node_ids(n_levels);
+    pl.node_ids.assign(n_levels, {});
+    std::vector<std::vector<uint32_t>>& node_ids = pl.node_ids;
     std::vector<std::map<uint32_t, std::vector<uint32_t>>> adj(n_levels);
     for (const Tuple& t : idx_rows) {
       int64_t layer;
@@ -287,41 +526,52 @@ struct StagedHnswIndex {
       n_edges_kept++;
     }
     // vectors (VectorCache::ensure_key, hnsw.rs:122-151)
-    std::vector<float> vectors((size_t)n * mf.vec_dim);
+    pl.vectors.resize((size_t)n * mf.vec_dim);
+    std::vector<float>& vectors = pl.vectors;
     for (uint32_t i = 0; i < n; ++i) fetch(keys[i], vectors.data() + (size_t)i * mf.vec_dim);
-    // flatten to the C ABI descriptor
-    std::vector<CozoGpuHnswLevel> levels(n_levels);
-    std::vector<std::vector<uint64_t>> row_ptr(n_levels);
-    std::vector<std::vector<uint32_t>> col_idx(n_levels);
+    // flatten
+    pl.row_ptr.assign(n_levels, {});
+    pl.col_idx.assign(n_levels, {});
     for (uint32_t L = 0; L < n_levels; ++L) {
-      row_ptr[L].push_back(0);
+      pl.row_ptr[L].push_back(0);
       if (L == 0) {
         for (uint32_t i = 0; i < n; ++i) {
           auto it = adj[0].find(i);
-          if (it != adj[0].end()) col_idx[0].insert(col_idx[0].end(), it->second.begin(), it->second.end());
-          row_ptr[0].push_back(col_idx[0].size());
+          if (it != adj[0].end()) pl.col_idx[0].insert(pl.col_idx[0].end(), it->second.begin(), it->second.end());
+          pl.row_ptr[0].push_back(pl.col_idx[0].size());
         }
       } else {
         for (auto& kv : adj[L]) {
           node_ids[L].push_back(kv.first);
-          col_idx[L].insert(col_idx[L].end(), kv.second.begin(), kv.second.end());
-          row_ptr[L].push_back(col_idx[L].size());
+          pl.col_idx[L].insert(pl.col_idx[L].end(), kv.second.begin(), kv.second.end());
+          pl.row_ptr[L].push_back(pl.col_idx[L].size());
         }
       }
-      levels[L].n_nodes = L == 0 ? n : (uint32_t)node_ids[L].size();
-      levels[L].node_ids = L == 0 ? nullptr : node_ids[L].data();
-      levels[L].row_ptr = row_ptr[L].data();
-      levels[L].col_idx = col_idx[L].data();
     }
+    return pl;
+  }
+
+  // hand a plan to the device (cozo_gpu_hnsw_stage) and adopt its dictionary
+  void upload(StagePlan pl, const HnswIndexManifest& mf) {
+    manifest = mf;
+    const uint32_t n = (uint32_t)pl.keys.size();
+    std::vector<CozoGpuHnswLevel> levels(pl.n_levels);
+    for (uint32_t L = 0; L < pl.n_levels; ++L) {
+      levels[L].n_nodes = L == 0 ? n : (uint32_t)pl.node_ids[L].size();
+      levels[L].node_ids = L == 0 ? nullptr : pl.node_ids[L].data();
+      levels[L].row_ptr = pl.row_ptr[L].data();
+      levels[L].col_idx = pl.col_idx[L].data();
+    }
+    float dummy = 0;
     CozoGpuHnswStageDesc d{};
     d.n_vectors = n;
     d.dim = (uint32_t)mf.vec_dim;
     d.metric = (int32_t)mf.distance;
-    d.n_levels = n_levels;
+    d.n_levels = pl.n_levels;
     d.levels = levels.data();
-    d.vectors = vectors.data();
+    d.vectors = n ? pl.vectors.data() : &dummy;
     d.vectors_on_device = 0;
-    d.entry_point = entry;
+    d.entry_point = pl.entry;
     d.m_max0 = (uint32_t)mf.m_max0;
     d.m_max = (uint32_t)mf.m_max;
     if (h) {
@@ -329,6 +579,12 @@ struct StagedHnswIndex {
       h = nullptr;
     }
     gpu_check(cozo_gpu_hnsw_stage(&h, &d));
+    keys = std::move(pl.keys);
+    key_ids.clear();
+    live.clear();
+    n_edges_kept = pl.n_edges_kept;
+    n_rows_dropped_same_key = pl.n_rows_dropped_same_key;
+    n_rows_dropped_ignored = pl.n_rows_dropped_ignored;
   }
 
   // create_hnsw_index (runtime/relation.rs:1010-1201): index every vector of the base relation in key

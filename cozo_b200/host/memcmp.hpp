@@ -205,6 +205,56 @@ inline size_t decode_datavalue(const uint8_t* p, size_t n, DataValue& out) {
   }
 }
 
+// Encoded length of one value without materialising it (the stager walks index keys with this)
+inline size_t skip_datavalue(const uint8_t* p, size_t n) {
+  if (n == 0) throw CozoError("", "truncated key");
+  switch (p[0]) {
+    case NULL_TAG:
+    case FALSE_TAG:
+    case TRUE_TAG:
+    case BOT_TAG: return 1;
+    case NUM_TAG: {
+      if (n < 10) throw CozoError("", "truncated number");
+      const uint8_t t = p[9];
+      if (t == IS_FLOAT || t == IS_EXACT_INT) return 10;
+      if (t == IS_APPROX_INT) {
+        if (n < 18) throw CozoError("", "truncated number");
+        return 18;
+      }
+      throw CozoError("", "corrupt number tag");
+    }
+    case STR_TAG:
+    case BYTES_TAG: {
+      size_t off = 1;
+      for (;;) {
+        if (off + ENC_GROUP_SIZE + 1 > n) throw CozoError("", "truncated memcmp bytes");
+        const uint8_t marker = p[off + ENC_GROUP_SIZE];
+        off += ENC_GROUP_SIZE + 1;
+        if (marker != ENC_MARKER) {
+          if ((size_t)(ENC_MARKER - marker) > ENC_GROUP_SIZE) throw CozoError("", "corrupt memcmp bytes");
+          return off;
+        }
+      }
+    }
+    case LIST_TAG: {
+      size_t off = 1;
+      for (;;) {
+        if (off >= n) throw CozoError("", "truncated list");
+        if (p[off] == INIT_TAG) return off + 1;
+        off += skip_datavalue(p + off, n - off);
+      }
+    }
+    case VEC_TAG: {
+      if (n < 10) throw CozoError("", "truncated vector");
+      if (p[1] != VEC_F32 && p[1] != VEC_F64) throw CozoError("", "corrupt vector tag");
+      const size_t total = 10 + (size_t)get_u64_be(p + 2) * (p[1] == VEC_F32 ? 4 : 8);
+      if (n < total) throw CozoError("", "truncated vector");
+      return total;
+    }
+    default: throw CozoError("", "unsupported memcmp tag " + std::to_string((int)p[0]));
+  }
+}
+
 // TupleT::encode_as_key (tuple.rs:29-38): 8-byte big-endian relation id, then the values
 inline std::string encode_as_key(const Tuple& t, uint64_t relation_id) {
   std::string o;

@@ -364,6 +364,23 @@ inline void extend_tuple_from_v(Tuple& key, const std::string& val, bool lenient
   if (r.p != r.end) throw CozoError("", "trailing bytes after the value columns");
 }
 
+// One Bool value column of a stored value without materialising the row (the stager reads `ignore_link`
+// with it).  A column that is not a Bool reads as false, like DataValue::get_bool on the decoded tuple.
+inline bool read_bool_column(const std::string& val, size_t col) {
+  if (val.size() < 8) throw CozoError("", "value shorter than the relation id prefix");
+  Reader r(reinterpret_cast<const uint8_t*>(val.data()) + 8, val.size() - 8);
+  const size_t n = r.read_array_len();
+  if (col >= n) throw CozoError("", "value column out of range");
+  for (size_t i = 0; i < col; ++i) r.skip();
+  const uint8_t t = r.peek();
+  if (!((t >= 0x80 && t <= 0x8f) || t == 0xde || t == 0xdf)) return false;  // a unit variant (Null, Bot)
+  if (r.read_map_len() != 1) throw CozoError("", "msgpack: enum must be a 1-entry map");
+  if (read_variant(r, datavalue_variants(), 13) != "Bool") return false;
+  const uint8_t b = (uint8_t)r.be(1);
+  if (b != 0xc2 && b != 0xc3) throw CozoError("", "msgpack: expected a bool");
+  return b == 0xc3;
+}
+
 // Fast path of the stager: copy ONE f32 vector column (and optionally one element of a
 // list-of-vectors column, sub_idx >= 0) of a stored value into `out[dim]` without materialising the
 // row — VectorCache::ensure_key (hnsw.rs:122-151) against raw KV bytes.  `col` counts value columns.

@@ -5,6 +5,8 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <chrono>
+
 #include "hnsw.hpp"
 #include "memcmp.hpp"
 
@@ -112,6 +114,18 @@ struct PyRelation {
   size_t size() const { return rel.rows.size(); }
 };
 
+static KvRelation load_kv(py::handle h, uint64_t id, size_t nk) {
+  KvRelation r;
+  r.id = id;
+  r.n_keys = nk;
+  for (auto item : h) {
+    auto t = item.cast<py::tuple>();
+    r.kv.emplace_back(t[0].cast<std::string>(), t[1].cast<std::string>());
+  }
+  std::sort(r.kv.begin(), r.kv.end());
+  return r;
+}
+
 struct PyHnswIndex {
   StagedHnswIndex ix;
   void stage(const PyRelation& base, py::handle idx_rows, py::dict mf) {
@@ -133,18 +147,7 @@ struct PyHnswIndex {
   }
   // the same from KV bytes: lists of (key bytes, value bytes) as a storage range scan yields them
   void stage_kv(py::handle base_kv, uint64_t base_id, size_t n_keys, py::handle idx_kv, uint64_t idx_id, py::dict mf) {
-    auto load = [](py::handle h, uint64_t id, size_t nk) {
-      KvRelation r;
-      r.id = id;
-      r.n_keys = nk;
-      for (auto item : h) {
-        auto t = item.cast<py::tuple>();
-        r.kv.emplace_back(t[0].cast<std::string>(), t[1].cast<std::string>());
-      }
-      std::sort(r.kv.begin(), r.kv.end());
-      return r;
-    };
-    KvRelation b = load(base_kv, base_id, n_keys), i = load(idx_kv, idx_id, 0);
+    KvRelation b = load_kv(base_kv, base_id, n_keys), i = load_kv(idx_kv, idx_id, 0);
     ix.stage_kv(b, i, manifest_of(mf));
   }
   static HnswIndexManifest manifest_of(py::dict mf) {
@@ -184,6 +187,30 @@ struct PyHnswIndex {
     return d;
   }
 };
+
+// a StagePlan as plain Python objects (host-only: no device call), for the planner equivalence tests
+static py::dict plan_to_py(const StagePlan& pl) {
+  py::dict d;
+  py::list keys;
+  for (auto& ck : pl.keys) keys.append(py::make_tuple(from_tuple(std::get<0>(ck)), std::get<1>(ck), std::get<2>(ck)));
+  d["keys"] = keys;
+  d["entry"] = pl.entry;
+  d["n_levels"] = pl.n_levels;
+  py::list ni, rp, ci;
+  for (uint32_t L = 0; L < pl.n_levels; ++L) {
+    ni.append(py::array_t<uint32_t>(pl.node_ids[L].size(), pl.node_ids[L].data()));
+    rp.append(py::array_t<uint64_t>(pl.row_ptr[L].size(), pl.row_ptr[L].data()));
+    ci.append(py::array_t<uint32_t>(pl.col_idx[L].size(), pl.col_idx[L].data()));
+  }
+  d["node_ids"] = ni;
+  d["row_ptr"] = rp;
+  d["col_idx"] = ci;
+  d["vectors"] = py::array_t<float>(pl.vectors.size(), pl.vectors.data());
+  d["edges_kept"] = pl.n_edges_kept;
+  d["dropped_same_key"] = pl.n_rows_dropped_same_key;
+  d["dropped_ignore_link"] = pl.n_rows_dropped_ignored;
+  return d;
+}
 
 struct PyHnswSearchRA {
   HnswSearchRA ra;
@@ -312,6 +339,84 @@ PYBIND11_MODULE(_cozo_host, m) {
     py::array_t<float> out(dim);
     msgpack_codec::extract_vector(v, col, sub, out.mutable_data(), dim);
     return out;
+  });
+  // staging plans (host only): from tuples, from KV bytes via tuples, from KV bytes directly
+  m.def("plan_stage", [](const PyRelation& base, py::handle idx_rows, py::dict mf) {
+    HnswIndexManifest m = PyHnswIndex::manifest_of(mf);
+    const RelationHandle& rel = base.rel;
+    return plan_to_py(StagedHnswIndex::plan_with(rel.keys.size(), to_rows(idx_rows), m, [&](const CompoundKey& ck, float* out) {
+      const Tuple* row = rel.get(std::get<0>(ck));
+      if (!row) throw CozoError("", "Cannot find compound key for HNSW");
+      const DataValue* field = &(*row)[std::get<1>(ck)];
+      if (std::get<2>(ck) >= 0) field = &field->list.at((size_t)std::get<2>(ck));
+      if (field->kind != DataValue::Vec || field->v->size() != m.vec_dim) throw CozoError("", "Cannot interpret value as vector");
+      std::copy(field->v->begin(), field->v->end(), out);
+    }));
+  });
+  m.def("plan_stage_kv", [](py::handle base_kv, uint64_t base_id, size_t n_keys, py::handle idx_kv, uint64_t idx_id, py::dict mf,
+                            bool bytes_level) {
+    KvRelation b = load_kv(base_kv, base_id, n_keys), i = load_kv(idx_kv, idx_id, 0);
+    HnswIndexManifest m = PyHnswIndex::manifest_of(mf);
+    return plan_to_py(bytes_level ? StagedHnswIndex::plan_kv_bytes(b, i, m) : StagedHnswIndex::plan_kv_tuples(b, i, m));
+  }, py::arg("base_kv"), py::arg("base_id"), py::arg("n_keys"), py::arg("idx_kv"), py::arg("idx_id"), py::arg("mf"),
+     py::arg("bytes_level") = true);
+  // throughput of the two KV planners on a synthetic index (n vectors, `deg` neighbours each, int keys)
+  m.def("bench_stage_kv", [](uint32_t n, uint32_t dim, uint32_t deg, bool bytes_level) {
+    RelationHandle base;
+    base.name = "b";
+    base.keys = {"k"};
+    base.non_keys = {"v"};
+    std::vector<Tuple> idx_rows;
+    uint64_t x = 88172645463325252ull;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (uint32_t i = 0; i < n; ++i) {
+      std::vector<float> v(dim);
+      for (auto& e : v) e = (float)(rnd() % 1000) / 1000.f;
+      base.put({DataValue::from_int(i), DataValue::from_vec(std::move(v))});
+      auto row = [&](uint32_t to, double d, bool self) {
+        return Tuple{DataValue::from_int(0), DataValue::from_int(i), DataValue::from_int(1), DataValue::from_int(-1),
+                     DataValue::from_int(to), DataValue::from_int(1), DataValue::from_int(-1), DataValue::from_float(d),
+                     self ? DataValue::from_bytes(std::string(32, 'h')) : DataValue::null(), DataValue::from_bool(false)};
+      };
+      idx_rows.push_back(row(i, (double)deg, true));
+      for (uint32_t j = 0; j < deg; ++j) {
+        uint32_t to = (uint32_t)(rnd() % n);
+        if (to != i) idx_rows.push_back(row(to, 0.5, false));
+      }
+    }
+    Tuple canary{DataValue::from_int(1)};
+    for (int c = 0; c < 6; ++c) canary.push_back(DataValue::null());
+    canary.push_back(DataValue::from_int(0));
+    canary.push_back(DataValue::from_bytes("c"));
+    canary.push_back(DataValue::from_bool(false));
+    idx_rows.push_back(canary);
+    KvRelation bkv = KvRelation::encode(base, 11), ikv;
+    ikv.id = 12;
+    for (auto& t : idx_rows) {
+      Tuple k(t.begin(), t.begin() + 7);
+      ikv.kv.emplace_back(memcmp_codec::encode_as_key(k, 12), msgpack_codec::encode_vals(t, 7, 12));
+    }
+    std::sort(ikv.kv.begin(), ikv.kv.end());
+    ikv.kv.erase(std::unique(ikv.kv.begin(), ikv.kv.end(), [](auto& a, auto& b) { return a.first == b.first; }), ikv.kv.end());
+    HnswIndexManifest m;
+    m.vec_dim = dim;
+    m.m_neighbours = deg / 2;
+    m.vec_fields = {1};
+    m.derive();
+    size_t bytes = 0;
+    for (auto& kv : ikv.kv) bytes += kv.first.size() + kv.second.size();
+    for (auto& kv : bkv.kv) bytes += kv.first.size() + kv.second.size();
+    auto t0 = std::chrono::steady_clock::now();
+    StagePlan pl = bytes_level ? StagedHnswIndex::plan_kv_bytes(bkv, ikv, m) : StagedHnswIndex::plan_kv_tuples(bkv, ikv, m);
+    double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    py::dict d;
+    d["index_rows"] = ikv.kv.size();
+    d["vectors"] = pl.keys.size();
+    d["edges_kept"] = pl.n_edges_kept;
+    d["kv_bytes"] = bytes;
+    d["seconds"] = s;
+    d["index_rows_per_s"] = (double)ikv.kv.size() / s;
+    return d;
   });
   m.def("relation_to_kv", [](const PyRelation& rel, uint64_t id) {
     KvRelation r = KvRelation::encode(rel.rel, id);
