@@ -880,6 +880,11 @@ extern "C" int cozo_gpu_hnsw_insert(cozo_gpu_hnsw_t* h, const float* vectors, ui
   if (rc) return rc;
   if (first_id) *first_id = h->dev.n;
   if (count == 0) return 0;
+  // A handle staged from the canary row alone has none of the builder's arrays: its first vectors go through
+  // cozo_gpu_hnsw_build (what the host layer does, StagedHnswIndex::put_rows).  Growing it in place faulted in
+  // the close-out run of round 1 and is refused until that is fixed.
+  if (h->dev.n == 0)
+    return set_error(COZO_GPU_EUNSUP, "insert into an empty index: create it with cozo_gpu_hnsw_build");
   if (h->m_max < 2 || h->m_max > 64) return set_error(COZO_GPU_EUNSUP, "m_neighbours must be in [2,64] for the device builder");
   if (ef_construction) h->ef_construction = ef_construction;
   if (h->ef_construction == 0) return set_error(COZO_GPU_EINVAL, "ef_construction must be set");

@@ -765,7 +765,9 @@ struct StagedHnswIndex {
               [](const auto& a, const auto& b) { return CompoundKeyLess()(a.first, b.first); });
     const bool in_order = appended.empty() || key_ids.empty() || CompoundKeyLess()(key_ids.rbegin()->first, appended.front().first);
     for (const Tuple& row : rows) base.put(row);
-    if (!in_order) {  // a new key lands inside the indexed key range: re-index (ids must stay in key order)
+    // a new key lands inside the indexed key range (ids must stay in key order), or nothing is indexed yet
+    // (then this is create_hnsw_index over the rows just stored): re-index from the base relation
+    if (!in_order || (keys.empty() && !appended.empty())) {
       n_rebuilt++;
       build(base, manifest);
       if (filter) {

@@ -160,7 +160,8 @@ int cozo_gpu_hnsw_build(cozo_gpu_hnsw_t** out, const CozoGpuHnswBuildDesc* desc)
  * insert = hnsw_put for rows whose keys sort after every indexed key (query/stored.rs:332 ->
  * hnsw.rs:679-727): the vectors get the dense ids [n, n+count) (*first_id = n), levels from the
  * handle's seeded level law; ef_construction 0 / keep_pruned < 0 keep the handle's settings
- * (a staged index has none: pass them).  remove = hnsw_remove (hnsw.rs:728-868): the nodes'
+ * (a staged index has none: pass them).  An EMPTY index (n = 0, staged from the canary row alone)
+ * is refused with COZO_GPU_EUNSUP: its first vectors go through cozo_gpu_hnsw_build.  remove = hnsw_remove (hnsw.rs:728-868): the nodes'
  * rows are deleted on every layer together with every edge that points at them; if the entry
  * point goes, the first remaining row in key order takes over (hnsw.rs:828-865). */
 int cozo_gpu_hnsw_insert(cozo_gpu_hnsw_t* h, const float* vectors, uint32_t count, int32_t vectors_on_device,

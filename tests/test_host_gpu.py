@@ -442,3 +442,29 @@ def test_put_and_rm_on_an_indexed_relation(h):
     a = h.HnswSearchRA(base, index, k=5, ef=40, bind_distance=True, bind_idx=0).iter([[q] for q in Q])
     b = h.HnswSearchRA(base, fresh, k=5, ef=40, bind_distance=True, bind_idx=0).iter([[q] for q in Q])
     assert [(r[1], r[4]) for r in a] == [(r[1], r[4]) for r in b] and len(a) == 300
+
+
+def test_put_into_an_empty_index(h, gpu):
+    """`::hnsw create` on an empty relation, then `:put`: the first rows index through the build path."""
+    dim, m = 16, 6
+    X = uniform_vectors(500, dim, 91)
+    mf = {"dim": dim, "m": m, "ef_construction": 40, "fields": [1]}
+    base = h.Relation("a", ["k"], ["v"])
+    index = h.HnswIndex()
+    index.build(base, mf)                                              # canary only
+    assert h.HnswSearchRA(base, index, k=3, ef=20, bind_idx=0).iter([[X[0]]]) == []
+    index.put_rows(base, [[i, X[i]] for i in range(300)])
+    index.put_rows(base, [[i, X[i]] for i in range(300, 500)])         # now an append
+    info = index.info()
+    assert info["n_vectors"] == 500 and info["put_appended"] == 200
+    out = h.HnswSearchRA(base, index, k=1, ef=40, bind_distance=True, bind_idx=0).iter([[x] for x in X])
+    assert sum(r[1] == i and r[3] == 0.0 for i, r in enumerate(out)) >= 490
+    # C ABI: growing a handle staged from the canary alone is refused before any device work (cozo_gpu.h):
+    # its first vectors go through cozo_gpu_hnsw_build, which is what put_rows did above
+    e = gpu.HnswIndex.stage(np.zeros((0, dim), np.float32), [None], [np.zeros(1, np.uint64)], [np.zeros(0, np.uint32)],
+                            0xFFFFFFFF, m_max0=2 * m, m_max=m)
+    with pytest.raises(gpu.CozoGpuError) as err:
+        e.insert(X[:200], ef_construction=40)
+    assert err.value.code == gpu.E_UNSUP
+    ids, dist, cnt, _ = e.search(X[:4], 1, 40)
+    assert (cnt == 0).all()                                            # still a valid, empty index
