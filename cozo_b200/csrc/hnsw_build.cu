@@ -552,19 +552,23 @@ int hnsw_ensure_build_state(cozo_gpu_hnsw* h) {
   // staging allocated exactly n rows; move to the growable layout
   if (h->cap_n == 0) {
     h->cap_n = g.n;
-    h->cap_up = std::max<uint64_t>(h->up_rows, 1);
+    // capacity == live rows exactly: the arrays staging made have no slack, and hnsw_reserve's grow() treats
+    // everything below the capacity as initialised (a capacity of 1 with 0 live upper rows would carry one
+    // row of uninitialised ids and degrees into the grown arrays)
+    h->cap_up = h->up_rows;
     uint32_t* p32 = nullptr;
     float* pf = nullptr;
     uint8_t* p8 = nullptr;
+    const size_t up_alloc = std::max<size_t>((size_t)h->cap_up, 1);
     H_CUDA(cudaMalloc(&pf, std::max<size_t>((size_t)h->cap_n * g.s0, 1) * 4));
     h->d_adj0_dist = pf;
-    H_CUDA(cudaMalloc(&pf, (size_t)h->cap_up * g.su * 4));
+    H_CUDA(cudaMalloc(&pf, up_alloc * g.su * 4));
     h->d_adj_up_dist = pf;
     H_CUDA(cudaMalloc(&p32, std::max<size_t>(h->cap_n, 1) * 4));
     h->d_deg0 = p32;
-    H_CUDA(cudaMalloc(&p32, (size_t)h->cap_up * 4));
+    H_CUDA(cudaMalloc(&p32, up_alloc * 4));
     h->d_deg_up = p32;
-    H_CUDA(cudaMalloc(&p32, (size_t)h->cap_up * 4));
+    H_CUDA(cudaMalloc(&p32, up_alloc * 4));
     h->d_up_owner = p32;
     H_CUDA(cudaMalloc(&p8, std::max<size_t>(h->cap_n, 1)));
     h->d_node_level = p8;
@@ -572,11 +576,11 @@ int hnsw_ensure_build_state(cozo_gpu_hnsw* h) {
     h->d_dead = p8;
     H_CUDA(cudaMemset(h->d_dead, 0, std::max<size_t>(h->cap_n, 1)));
     if (g.n) H_CUDA(cudaMemcpy(h->d_node_level, h->node_level.data(), g.n, cudaMemcpyHostToDevice));
-    std::vector<uint32_t> owner(h->cap_up, NONE);
+    std::vector<uint32_t> owner(up_alloc, NONE);
     uint64_t r = 0;
     for (uint32_t i = 0; i < g.n; ++i)
       for (uint32_t L = 0; L < h->node_level[i]; ++L) owner[r++] = i;
-    H_CUDA(cudaMemcpy(h->d_up_owner, owner.data(), (size_t)h->cap_up * 4, cudaMemcpyHostToDevice));
+    H_CUDA(cudaMemcpy(h->d_up_owner, owner.data(), up_alloc * 4, cudaMemcpyHostToDevice));
     h->live.assign(g.n, 1);
     h->n_live = g.n;
   }
