@@ -139,6 +139,27 @@ def ncu_traffic():
         return None
 
 
+
+def host_cores() -> int:
+    """threads the CPU arms may use: the affinity mask, capped by a cgroup CPU quota if one is set"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                quota, period = txt[0], float(txt[1])
+            else:
+                quota, period = txt[0], float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota not in ("max", "-1") and period > 0:
+                n = max(1, min(n, int(-(-float(quota) // period))))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
+
 def cpu_oracle_qps(X, levels, Q, k, ef, threads):
     from oracle import oracle as O
     ix = O.OracleHnsw.from_levels(X, O.HnswLevels(*levels))
@@ -154,7 +175,7 @@ def run_reference(a, rank, world):
     if rank != 0:
         return
     from cozo_b200 import capi
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     X = gen_vectors(a.n, a.dim, 0x5EED0001)
     capi.init(0)
     t0 = time.perf_counter()
@@ -328,7 +349,7 @@ def main():
     cpu_baseline = None
     recall_vs_oracle = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         levels = g.export_levels()
         sample = min(a.cpu_sample, B)
         s_last = a.warmup + a.steps - 1
