@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libcozo_gpu.so")
-SOURCES = ["common.cu", "hnsw.cu", "hnsw_build.cu", "graph.cu", "merge.cu"]
+SOURCES = ["common.cu", "hnsw.cu", "hnsw_build.cu", "graph.cu", "merge.cu", "sharded.cu"]
 HEADERS = ["common.cuh", "hnsw_device.cuh", "hnsw_host.hpp", os.path.join("..", "..", "include", "cozo_gpu.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(log, file=sys.stderr)
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in srcs]
     if force or jobs or _stale(OUT, objs):
-        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

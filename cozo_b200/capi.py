@@ -27,7 +27,10 @@ EXPORTS = [
     "cozo_gpu_hnsw_export_level", "cozo_gpu_hnsw_export_level_dist", "cozo_gpu_hnsw_export_live", "cozo_gpu_hnsw_vectors_dev", "cozo_gpu_topk_merge_dev", "cozo_gpu_graph_stage",
     "cozo_gpu_graph_free", "cozo_gpu_graph_export", "cozo_gpu_pagerank", "cozo_gpu_sssp_multi", "cozo_gpu_closeness",
     "cozo_gpu_betweenness", "cozo_gpu_clustering", "cozo_gpu_sssp_paths",
+    "cozo_gpu_shards_unique_id", "cozo_gpu_shards_init", "cozo_gpu_shards_free", "cozo_gpu_shards_info",
+    "cozo_gpu_hnsw_stage_sharded", "cozo_gpu_hnsw_search_sharded", "cozo_gpu_hnsw_search_sharded_dev",
 ]
+UID_BYTES = 128
 
 
 class CozoGpuError(RuntimeError):
@@ -104,6 +107,14 @@ def load():
     L.cozo_gpu_betweenness.argtypes = [vp, vp, vp, vp]
     L.cozo_gpu_clustering.argtypes = [vp, vp, vp, vp, vp, vp]
     L.cozo_gpu_sssp_paths.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.cozo_gpu_shards_unique_id.argtypes = [vp]
+    L.cozo_gpu_shards_init.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int]
+    L.cozo_gpu_shards_free.argtypes = [vp]
+    L.cozo_gpu_shards_free.restype = None
+    L.cozo_gpu_shards_info.argtypes = [vp, vp, vp, vp, vp]
+    L.cozo_gpu_hnsw_stage_sharded.argtypes = [vp, vp, vp, vp]
+    L.cozo_gpu_hnsw_search_sharded.argtypes = [vp, vp, u32, u32, u32, f64, C.c_int, vp, vp, vp, C.POINTER(SearchStats)]
+    L.cozo_gpu_hnsw_search_sharded_dev.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -301,6 +312,71 @@ class HnswIndex:
     def close(self):
         if self._h:
             load().cozo_gpu_hnsw_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardGroup:
+    """Owner of a cozo_gpu_shards_t: the ranks (one process per GPU) that hold the shards of one corpus.
+    `uid` = ShardGroup.unique_id() of ONE rank, handed to the others by any host channel."""
+
+    def __init__(self, uid: bytes, rank: int, world: int):
+        assert len(uid) == UID_BYTES
+        self._uid = (C.c_uint8 * UID_BYTES).from_buffer_copy(uid)
+        h = C.c_void_p()
+        _check(load().cozo_gpu_shards_init(C.byref(h), self._uid, rank, world))
+        self._h = h
+        self.rank, self.world = rank, world
+        self.index = None
+        self.offset = self.total_rows = 0
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * UID_BYTES)()
+        _check(load().cozo_gpu_shards_unique_id(buf))
+        return bytes(buf)
+
+    def attach(self, index: "HnswIndex"):
+        """collective: this rank's shard; -> (global id of its row 0, rows of the whole corpus)"""
+        off, tot = C.c_uint64(), C.c_uint64()
+        _check(load().cozo_gpu_hnsw_stage_sharded(self._h, index._h, C.byref(off), C.byref(tot)))
+        self.index = index
+        self.offset, self.total_rows = off.value, tot.value
+        return off.value, tot.value
+
+    def info(self):
+        r, w, x, t = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+        _check(load().cozo_gpu_shards_info(self._h, C.byref(r), C.byref(w), C.byref(x), C.byref(t)))
+        return {"rank": r.value, "world": w.value, "exchange": "fused" if x.value else "nccl", "total_rows": t.value}
+
+    def search(self, queries, k: int, ef: int, radius: float | None = None, root: int = -1, B: int | None = None):
+        """collective host-buffer call -> global ids[B,k] u64 (UINT64_MAX padded), dist[B,k], count[B], stats"""
+        if queries is not None:
+            queries = np.ascontiguousarray(queries, np.float32).reshape(-1, self.index.dim)
+            B = queries.shape[0]
+        ids = np.empty((B, max(k, 1)), np.uint64)
+        dist = np.empty((B, max(k, 1)), np.float32)
+        cnt = np.zeros(B, np.uint32)
+        st = SearchStats()
+        _check(load().cozo_gpu_hnsw_search_sharded(self._h, _p(queries), B, k, ef,
+                                                   -1.0 if radius is None else float(radius), root, _p(ids), _p(dist),
+                                                   _p(cnt), C.byref(st)))
+        return ids, dist, cnt, st
+
+    def search_dev(self, q_ptr: int, B: int, k: int, ef: int, out_ids_ptr: int, out_dist_ptr: int,
+                   qstats_ptr: int | None = None, stream: int | None = None, radius: float | None = None):
+        _check(load().cozo_gpu_hnsw_search_sharded_dev(self._h, q_ptr, B, k, ef,
+                                                       -1.0 if radius is None else float(radius), out_ids_ptr,
+                                                       out_dist_ptr, qstats_ptr, stream))
+
+    def close(self):
+        if self._h:
+            load().cozo_gpu_shards_free(self._h)
             self._h = None
 
     def __del__(self):

@@ -289,13 +289,19 @@ static KernelFn pick_kernel(uint32_t ld, int metric, bool bulk) {
 static HnswWorkspace* new_ws();
 void hnsw_prewarm_pool(cozo_gpu_hnsw* h, size_t vis_words, size_t vlog_words);
 
-int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words) {
+// `stream` is the stream the next kernel using this workspace is launched on: a fresh bitmap is zeroed
+// there, i.e. ordered before that kernel (the legacy default stream does not order work of a
+// cudaStreamNonBlocking stream).
+int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words, cudaStream_t stream) {
   if (ws->vis_words < vis_words) {
-    if (ws->vis) cudaFree(ws->vis);
+    if (ws->vis) {
+      COZO_CUDA(cudaStreamSynchronize(stream));  // nothing may still read the old bitmap
+      cudaFree(ws->vis);
+    }
     ws->vis = nullptr;
     ws->vis_words = 0;
     COZO_CUDA(cudaMalloc(&ws->vis, vis_words * 4));
-    COZO_CUDA(cudaMemset(ws->vis, 0, vis_words * 4));
+    COZO_CUDA(cudaMemsetAsync(ws->vis, 0, vis_words * 4, stream));
     ws->vis_words = vis_words;
   }
   if (ws->vlog_words < vlog_words) {
@@ -356,7 +362,9 @@ void hnsw_prewarm_pool(cozo_gpu_hnsw* h, size_t vis_words, size_t vlog_words) {
       h->n_workspaces++;
     }
     HnswWorkspace* ws = new_ws();
-    if (!ws || hnsw_ws_reserve(ws, vis_words, vlog_words) != 0) {
+    // zeroed on the workspace's own stream and waited for: whichever stream uses it later sees zeros
+    if (!ws || hnsw_ws_reserve(ws, vis_words, vlog_words, ws->stream) != 0 ||
+        cudaStreamSynchronize(ws->stream) != cudaSuccess) {
       if (ws) hnsw_release_ws(h, ws);  // usable, just not pre-sized
       else {
         std::lock_guard<std::mutex> lk(h->mu);
@@ -426,7 +434,8 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
     if (smem > di.smem_optin)
       return set_error(COZO_GPU_EUNSUP, "ef=%u needs %zu B of shared memory per CTA (limit %zu)", ef, smem,
                        di.smem_optin);
-    COZO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // always the device maximum: concurrent callers with different ef / stages never lower each other's limit
+    COZO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.smem_optin));
     int cps = 0;
     COZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, fn, 128, smem));
     if (cps < 1) return set_error(COZO_GPU_ECUDA, "search kernel does not fit on an SM");
@@ -453,7 +462,7 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
     if (smem > di.smem_optin)
       return set_error(COZO_GPU_EUNSUP, "ef=%u needs %zu B of shared memory per warp (limit %zu)", ef, smem,
                        di.smem_optin);
-    COZO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COZO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.smem_optin));
     int ctas_per_sm = 0;
     COZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, wpc * 32, smem));
     if (ctas_per_sm < 1) return set_error(COZO_GPU_ECUDA, "search kernel does not fit on an SM");
@@ -468,7 +477,7 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
   uint32_t nwords = round_up((g.n + 31) / 32, 4);
   uint32_t logcap = std::min<uint32_t>(65536u, std::max<uint32_t>(4096u, 64u * ef));
   size_t slots = (size_t)grid * wpc;
-  int rc = hnsw_ws_reserve(ws, slots * nwords, slots * logcap);
+  int rc = hnsw_ws_reserve(ws, slots * nwords, slots * logcap, stream);
   if (rc) return rc;
   hnsw_prewarm_pool(h, slots * nwords, slots * logcap);  // first call only: no allocation in later calls
 

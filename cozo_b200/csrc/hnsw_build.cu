@@ -622,7 +622,7 @@ int hnsw_insert_range(cozo_gpu_hnsw* h, uint32_t begin, uint32_t end, uint32_t m
     smem1 = (size_t)lay.warp_bytes * wpc;
   }
   if (smem1 > di.smem_optin) return set_error(COZO_GPU_EUNSUP, "ef_construction=%u does not fit shared memory", ef_c);
-  H_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  H_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.smem_optin));
   int cps = 0;
   H_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, k1, wpc * 32, smem1));
   if (cps < 1) return set_error(COZO_GPU_ECUDA, "build kernel does not fit on an SM");
@@ -658,7 +658,7 @@ int hnsw_insert_range(cozo_gpu_hnsw* h, uint32_t begin, uint32_t end, uint32_t m
   const uint32_t logcap = std::min<uint32_t>(65536u, std::max<uint32_t>(4096u, 64u * ef_c));
   {
     size_t slots = (size_t)max_grid1 * wpc;
-    rc = hnsw_ws_reserve(ws, slots * nwords, slots * logcap);
+    rc = hnsw_ws_reserve(ws, slots * nwords, slots * logcap, st);
     if (rc) return rc;
   }
   max_batch = std::min<uint32_t>(max_batch, end - begin);
@@ -884,11 +884,8 @@ extern "C" int cozo_gpu_hnsw_insert(cozo_gpu_hnsw_t* h, const float* vectors, ui
   if (rc) return rc;
   if (first_id) *first_id = h->dev.n;
   if (count == 0) return 0;
-  // A handle staged from the canary row alone has none of the builder's arrays: its first vectors go through
-  // cozo_gpu_hnsw_build (what the host layer does, StagedHnswIndex::put_rows).  Growing it in place faulted in
-  // the close-out run of round 1 and is refused until that is fixed.
-  if (h->dev.n == 0)
-    return set_error(COZO_GPU_EUNSUP, "insert into an empty index: create it with cozo_gpu_hnsw_build");
+  // A handle staged from the canary row alone (n = 0) grows from empty arrays: hnsw_ensure_build_state gives it
+  // capacities equal to its live rows (0), so every row the first insert creates is initialised by grow().
   if (h->m_max < 2 || h->m_max > 64) return set_error(COZO_GPU_EUNSUP, "m_neighbours must be in [2,64] for the device builder");
   if (ef_construction) h->ef_construction = ef_construction;
   if (h->ef_construction == 0) return set_error(COZO_GPU_EINVAL, "ef_construction must be set");

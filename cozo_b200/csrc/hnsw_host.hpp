@@ -73,6 +73,6 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
                        cudaStream_t stream, const ScatterDest* scatter);
 HnswWorkspace* hnsw_acquire_ws(cozo_gpu_hnsw* h);
 void hnsw_release_ws(cozo_gpu_hnsw* h, HnswWorkspace* ws);
-int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words);
+int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words, cudaStream_t stream);
 int hnsw_ensure_build_state(cozo_gpu_hnsw* h);
 }  // namespace cozo

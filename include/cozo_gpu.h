@@ -161,7 +161,8 @@ int cozo_gpu_hnsw_build(cozo_gpu_hnsw_t** out, const CozoGpuHnswBuildDesc* desc)
  * hnsw.rs:679-727): the vectors get the dense ids [n, n+count) (*first_id = n), levels from the
  * handle's seeded level law; ef_construction 0 / keep_pruned < 0 keep the handle's settings
  * (a staged index has none: pass them).  An EMPTY index (n = 0, staged from the canary row alone)
- * is refused with COZO_GPU_EUNSUP: its first vectors go through cozo_gpu_hnsw_build.  remove = hnsw_remove (hnsw.rs:728-868): the nodes'
+ * grows in place: its first vector only gets its rows and becomes the entry point (hnsw.rs:360-373).
+ * remove = hnsw_remove (hnsw.rs:728-868): the nodes'
  * rows are deleted on every layer together with every edge that points at them; if the entry
  * point goes, the first remaining row in key order takes over (hnsw.rs:828-865). */
 int cozo_gpu_hnsw_insert(cozo_gpu_hnsw_t* h, const float* vectors, uint32_t count, int32_t vectors_on_device,
@@ -193,6 +194,43 @@ const float* cozo_gpu_hnsw_vectors_dev(cozo_gpu_hnsw_t* h, uint32_t* row_stride)
 int cozo_gpu_topk_merge_dev(const float* dist_dev, const uint32_t* ids_dev, uint32_t n_shards, uint32_t B,
                             uint32_t k, const uint64_t* shard_offsets_dev, uint64_t* out_ids_dev,
                             float* out_dist_dev, void* stream);
+
+/* ---- sharded corpus: one process per GPU, one shard (vectors + graph) per rank -------------
+ * SURVEY.md §8b "Multi-GPU" / §8e.  The reference answers a query from ONE index relation
+ * (query/ra.rs:1102-1119 -> runtime/hnsw.rs:869-1012); here the corpus is row-partitioned over the
+ * ranks, every rank searches its own shard and the per-shard top-k lists are exchanged and merged
+ * inside the library: broadcast + per-shard search + all-gather + merge behind one call.
+ * The communicator is NCCL's (resolved with dlopen at first use); its 128-byte unique id is created
+ * on one rank and handed to the others by any host channel the embedding process has. */
+typedef struct cozo_gpu_shards cozo_gpu_shards_t;
+#define COZO_GPU_UID_BYTES 128
+int cozo_gpu_shards_unique_id(uint8_t* id /* [COZO_GPU_UID_BYTES] */);
+/* collective over `world` ranks (each bound to its own device with cozo_gpu_init) */
+int cozo_gpu_shards_init(cozo_gpu_shards_t** out, const uint8_t* id, int rank, int world);
+void cozo_gpu_shards_free(cozo_gpu_shards_t* s);
+/* exchange: 0 = one NCCL all-gather per list, 1 = peer stores fused into the search kernel (CUDA IPC
+ * buffers over NVLink; chosen when every rank could map every peer, option "shard.exchange" = 0 forces NCCL) */
+int cozo_gpu_shards_info(cozo_gpu_shards_t* s, int* rank, int* world, int* exchange, uint64_t* total_rows);
+
+/* Collective.  Attach this rank's shard — staged with cozo_gpu_hnsw_stage or built with
+ * cozo_gpu_hnsw_build — to the communicator.  Shard r owns the global ids
+ * [offset_r, offset_r + n_vectors_r) of the row-contiguous partition. */
+int cozo_gpu_hnsw_stage_sharded(cozo_gpu_shards_t* s, cozo_gpu_hnsw_t* local_shard, uint64_t* out_global_offset,
+                                uint64_t* out_total_rows);
+
+/* Collective.  Batched hnsw_knn over the whole sharded corpus.  `queries` [B*dim] is host memory read on
+ * rank `root` and broadcast (root >= 0), or passed identically by every rank (root = -1).  Results on
+ * every rank that passes out buffers: out_ids [B*k] GLOBAL ids padded with UINT64_MAX, out_dist [B*k]
+ * padded with +inf, nearest first; out_count [B] nullable; stats (this rank's shard) nullable.
+ * The batch is processed in tiles of "shard.tile" queries (default 65536). */
+int cozo_gpu_hnsw_search_sharded(cozo_gpu_shards_t* s, const float* queries, uint32_t B, uint32_t k, uint32_t ef,
+                                 double radius, int root, uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                 CozoGpuSearchStats* stats);
+/* Same with the (replicated) batch and the outputs already in HBM; asynchronous, ordered after and
+ * before `stream`.  per_query_stats_dev nullable u32 [B*4]. */
+int cozo_gpu_hnsw_search_sharded_dev(cozo_gpu_shards_t* s, const float* queries_dev, uint32_t B, uint32_t k,
+                                     uint32_t ef, double radius, uint64_t* out_ids_dev, float* out_dist_dev,
+                                     uint32_t* per_query_stats_dev, void* stream);
 
 /* ---- graphs (FixedRule algorithms) -------------------------------------- */
 typedef struct cozo_gpu_graph cozo_gpu_graph_t;

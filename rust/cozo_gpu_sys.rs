@@ -6,6 +6,7 @@ use std::os::raw::{c_char, c_int, c_void};
 
 pub enum CozoGpuHnsw {}
 pub enum CozoGpuGraph {}
+pub enum CozoGpuShards {}
 
 pub const COZO_GPU_OK: c_int = 0;
 pub const COZO_GPU_EINVAL: c_int = -1;
@@ -16,6 +17,7 @@ pub const COZO_GPU_EKILLED: c_int = -5;
 pub const COZO_GPU_EUNSUP: c_int = -6;
 pub const COZO_GPU_NONE: u32 = 0xFFFF_FFFF;
 pub const COZO_GPU_MAX_PEERS: usize = 16;
+pub const COZO_GPU_UID_BYTES: usize = 128;
 pub const COZO_GPU_L2: i32 = 0;
 pub const COZO_GPU_COSINE: i32 = 1;
 pub const COZO_GPU_IP: i32 = 2;
@@ -92,6 +94,13 @@ extern "C" {
     pub fn cozo_gpu_hnsw_export_live(h: *mut CozoGpuHnsw, live: *mut u8) -> c_int;
     pub fn cozo_gpu_hnsw_vectors_dev(h: *mut CozoGpuHnsw, row_stride: *mut u32) -> *const f32;
     pub fn cozo_gpu_topk_merge_dev(dist_dev: *const f32, ids_dev: *const u32, n_shards: u32, B: u32, k: u32, shard_offsets_dev: *const u64, out_ids_dev: *mut u64, out_dist_dev: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn cozo_gpu_shards_unique_id(id: *mut u8) -> c_int;
+    pub fn cozo_gpu_shards_init(out: *mut *mut CozoGpuShards, id: *const u8, rank: c_int, world: c_int) -> c_int;
+    pub fn cozo_gpu_shards_free(s: *mut CozoGpuShards);
+    pub fn cozo_gpu_shards_info(s: *mut CozoGpuShards, rank: *mut c_int, world: *mut c_int, exchange: *mut c_int, total_rows: *mut u64) -> c_int;
+    pub fn cozo_gpu_hnsw_stage_sharded(s: *mut CozoGpuShards, local_shard: *mut CozoGpuHnsw, out_global_offset: *mut u64, out_total_rows: *mut u64) -> c_int;
+    pub fn cozo_gpu_hnsw_search_sharded(s: *mut CozoGpuShards, queries: *const f32, B: u32, k: u32, ef: u32, radius: f64, root: c_int, out_ids: *mut u64, out_dist: *mut f32, out_count: *mut u32, stats: *mut CozoGpuSearchStats) -> c_int;
+    pub fn cozo_gpu_hnsw_search_sharded_dev(s: *mut CozoGpuShards, queries_dev: *const f32, B: u32, k: u32, ef: u32, radius: f64, out_ids_dev: *mut u64, out_dist_dev: *mut f32, per_query_stats_dev: *mut u32, stream: *mut c_void) -> c_int;
     pub fn cozo_gpu_graph_stage(out: *mut *mut CozoGpuGraph, n: u32, m: u64, src: *const u32, dst: *const u32, w_or_null: *const f32) -> c_int;
     pub fn cozo_gpu_graph_free(g: *mut CozoGpuGraph);
     pub fn cozo_gpu_graph_export(g: *mut CozoGpuGraph, out_ptr: *mut u32, out_idx: *mut u32, out_w: *mut f32, in_ptr: *mut u32, in_idx: *mut u32) -> c_int;

@@ -51,24 +51,70 @@ def test_hnsw_1m_properties(gpu, big):
     assert np.array_equal(again[0], ids) and again[3].dist_evals == st.dist_evals
 
 
-def test_pagerank_rmat24_first_iteration(gpu):
-    """one pull iteration from the uniform start has a closed form: base + d*init*sum_{v in in(u)} 1/outdeg(v)"""
+@pytest.fixture(scope="module")
+def rmat24(gpu):
     import torch
     from tools.bench_pagerank import rmat_torch
     n, src, dst = rmat_torch(24, 16, 0x5EED0004)
     assert n == 1 << 24 and src.size == 1 << 28
     g = gpu.Graph(n, src, dst)
-    scores, it, err, ms = g.pagerank(0.85, 0.0, 1)
-    assert it == 1
     s = torch.from_numpy(src.view(np.int32)).cuda().long()
     d = torch.from_numpy(dst.view(np.int32)).cuda().long()
+    return n, src, dst, g, s, d, torch
+
+
+def _jacobi_f64(n, s, d, iters, torch, damping=np.float32(0.85)):
+    """the pull iteration of graph::page_rank (Jacobi schedule, SURVEY 8a8) in f64 with the f32 constants the
+    f32 implementations use (damping, base = (1-d)/n, init = 1/n): the ground truth both sides are judged by"""
+    damp = float(damping)
+    base = float((np.float32(1.0) - damping) / np.float32(n))
     outdeg = torch.bincount(s, minlength=n).double()
-    contrib = (1.0 / n) / outdeg
-    exp = torch.full((n,), 0.15 / n, dtype=torch.float64, device="cuda")
-    exp.index_add_(0, d, 0.85 * contrib[s])
+    x = torch.full((n,), float(np.float32(1.0) / np.float32(n)), dtype=torch.float64, device="cuda")
+    for _ in range(iters):
+        contrib = torch.where(outdeg > 0, x / outdeg, torch.zeros_like(x))
+        acc = torch.zeros(n, dtype=torch.float64, device="cuda")
+        acc.index_add_(0, d, contrib[s])
+        x = base + damp * acc
+    return x
+
+
+def test_pagerank_rmat24_first_iteration(gpu, rmat24):
+    """one pull iteration from the uniform start has a closed form: base + d*init*sum_{v in in(u)} 1/outdeg(v)"""
+    n, src, dst, g, s, d, torch = rmat24
+    scores, it, err, ms = g.pagerank(0.85, 0.0, 1)
+    assert it == 1
+    exp = _jacobi_f64(n, s, d, 1, torch)
     got = torch.from_numpy(scores).cuda().double()
     rel = ((got - exp).abs() / exp).max().item()
     assert rel <= 5e-6, rel
     # default options of the rule (theta .85, epsilon 1e-4, iterations 10): the iteration cap binds
     sc, it, err, _ = g.pagerank()
     assert it == 10 and np.all(np.isfinite(sc)) and sc.min() >= np.float32(0.15 / n) * (1 - 1e-6)
+
+
+def test_pagerank_rmat24_ten_iterations_vs_f64_truth(gpu, rmat24):
+    """BASELINE config 4 at the rule's defaults (10 iterations): the device scores are within 1e-5 rel of the f64
+    ground truth at EVERY node and at least as close to it as the oracle (the reference's sequential
+    `.sum::<f32>()` per row drifts on hub rows); device vs oracle differ by no more than the oracle's own error."""
+    import os
+    from oracle import oracle as O
+    n, src, dst, g, s, d, torch = rmat24
+    truth = _jacobi_f64(n, s, d, 10, torch)
+    scores, it, err, ms = g.pagerank(0.85, 0.0, 10)
+    assert it == 10
+    again = g.pagerank(0.85, 0.0, 10)[0]
+    assert np.array_equal(scores, again)                                    # run-to-run bit-identical
+    got = torch.from_numpy(scores).cuda().double()
+    rel_gpu = ((got - truth).abs() / truth)
+    assert rel_gpu.max().item() <= 1e-5, rel_gpu.max().item()
+    o = O.OracleGraph(n, src, dst)
+    os_, oit, _ = o.pagerank(0.85, 0.0, 10, n_threads=len(os.sched_getaffinity(0)))
+    assert oit == 10
+    orc = torch.from_numpy(os_).cuda().double()
+    rel_or = ((orc - truth).abs() / truth)
+    rel_go = ((got - orc).abs() / orc)
+    print(f"rmat24 x10: max rel err vs f64 truth: device {rel_gpu.max().item():.3e}, oracle {rel_or.max().item():.3e}; "
+          f"device vs oracle max {rel_go.max().item():.3e} p99.9 {torch.quantile(rel_go[:1 << 24:16].float(), 0.999).item():.3e}")
+    assert rel_gpu.max().item() <= rel_or.max().item() + 1e-7
+    assert rel_go.max().item() <= rel_or.max().item() + rel_gpu.max().item() + 1e-7   # triangle inequality, tight
+    assert (rel_go <= 1e-5).double().mean().item() >= 0.999                            # 1e-5 wherever the oracle is accurate

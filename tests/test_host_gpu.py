@@ -459,12 +459,20 @@ def test_put_into_an_empty_index(h, gpu):
     assert info["n_vectors"] == 500 and info["put_appended"] == 200
     out = h.HnswSearchRA(base, index, k=1, ef=40, bind_distance=True, bind_idx=0).iter([[x] for x in X])
     assert sum(r[1] == i and r[3] == 0.0 for i, r in enumerate(out)) >= 490
-    # C ABI: growing a handle staged from the canary alone is refused before any device work (cozo_gpu.h):
-    # its first vectors go through cozo_gpu_hnsw_build, which is what put_rows did above
+    # C ABI: a handle staged from the canary alone (n = 0) grows in place (hnsw.rs:360-373: the first vector
+    # only writes its self-loops and the canary); nodes all on layer 0 and nodes with upper layers both occur
     e = gpu.HnswIndex.stage(np.zeros((0, dim), np.float32), [None], [np.zeros(1, np.uint64)], [np.zeros(0, np.uint32)],
                             0xFFFFFFFF, m_max0=2 * m, m_max=m)
-    with pytest.raises(gpu.CozoGpuError) as err:
-        e.insert(X[:200], ef_construction=40)
-    assert err.value.code == gpu.E_UNSUP
     ids, dist, cnt, _ = e.search(X[:4], 1, 40)
-    assert (cnt == 0).all()                                            # still a valid, empty index
+    assert (cnt == 0).all()                                            # a valid, empty index
+    assert e.insert(X[:1], ef_construction=40) == 0                    # first vector alone
+    ids, dist, cnt, _ = e.search(X[:4], 2, 40)
+    assert (cnt == 1).all() and (ids[:, 0] == 0).all()
+    assert e.insert(X[1:300]) == 1
+    assert e.insert(X[300:]) == 300
+    n, _, nl, ep = e.info()
+    assert n == 500 and ep is not None
+    own, d0, _, _ = e.search(X, 1, 40)
+    assert (own[:, 0] == np.arange(500)).mean() >= 0.98 and (d0[own[:, 0] == np.arange(500), 0] == 0).all()
+    _, rp, ci, _ = e.export_levels()
+    assert np.diff(rp[0].astype(np.int64)).max() <= 2 * m and ci[0].max() < 500
