@@ -29,6 +29,7 @@ EXPORTS = [
     "cozo_gpu_betweenness", "cozo_gpu_clustering", "cozo_gpu_sssp_paths",
     "cozo_gpu_shards_unique_id", "cozo_gpu_shards_init", "cozo_gpu_shards_free", "cozo_gpu_shards_info",
     "cozo_gpu_hnsw_stage_sharded", "cozo_gpu_hnsw_search_sharded", "cozo_gpu_hnsw_search_sharded_dev",
+    "cozo_gpu_hnsw_search_filtered", "cozo_gpu_hnsw_search_filtered_dev",
 ]
 UID_BYTES = 128
 
@@ -107,6 +108,8 @@ def load():
     L.cozo_gpu_betweenness.argtypes = [vp, vp, vp, vp]
     L.cozo_gpu_clustering.argtypes = [vp, vp, vp, vp, vp, vp]
     L.cozo_gpu_sssp_paths.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.cozo_gpu_hnsw_search_filtered.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, C.POINTER(SearchStats)]
+    L.cozo_gpu_hnsw_search_filtered_dev.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, vp, vp]
     L.cozo_gpu_shards_unique_id.argtypes = [vp]
     L.cozo_gpu_shards_init.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int]
     L.cozo_gpu_shards_free.argtypes = [vp]
@@ -142,6 +145,15 @@ def set_option(name: str, value: int):
 
 def get_option(name: str) -> int:
     return load().cozo_gpu_get_option(name.encode())
+
+
+def pack_row_mask(row_pass) -> np.ndarray:
+    """bool[n] -> u32 words, bit (id & 31) of word id >> 5"""
+    b = np.ascontiguousarray(row_pass, bool)
+    words = np.zeros((b.size + 31) // 32 + 1, np.uint32)
+    packed = np.packbits(b, bitorder="little")
+    words.view(np.uint8)[:packed.size] = packed
+    return words
 
 
 class HnswIndex:
@@ -282,8 +294,9 @@ class HnswIndex:
         p = load().cozo_gpu_hnsw_vectors_dev(self._h, C.byref(stride))
         return p, stride.value
 
-    def search(self, queries: np.ndarray, k: int, ef: int, radius: float | None = None):
+    def search(self, queries: np.ndarray, k: int, ef: int, radius: float | None = None, row_pass: np.ndarray | None = None):
         """Host-buffer call == the FFI the Rust HnswSearchRA glue makes.
+        row_pass: optional bool[n] filter verdicts per indexed row (the filtered form, trim to k after the filter).
         -> ids[B,k] u32, dist[B,k] f32, count[B] u32, SearchStats"""
         queries = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
         B = queries.shape[0]
@@ -291,8 +304,13 @@ class HnswIndex:
         dist = np.empty((B, max(k, 1)), np.float32)
         cnt = np.zeros(B, np.uint32)
         st = SearchStats()
-        _check(load().cozo_gpu_hnsw_search(self._h, _p(queries), B, k, ef, -1.0 if radius is None else float(radius),
-                                           _p(ids), _p(dist), _p(cnt), C.byref(st)))
+        r = -1.0 if radius is None else float(radius)
+        if row_pass is None:
+            _check(load().cozo_gpu_hnsw_search(self._h, _p(queries), B, k, ef, r, _p(ids), _p(dist), _p(cnt), C.byref(st)))
+        else:
+            mask = pack_row_mask(row_pass)
+            _check(load().cozo_gpu_hnsw_search_filtered(self._h, _p(queries), B, k, ef, r, _p(mask), _p(ids), _p(dist),
+                                                        _p(cnt), C.byref(st)))
         return ids, dist, cnt, st
 
     def search_dev(self, q_ptr: int, B: int, k: int, ef: int, ids_ptr: int, dist_ptr: int, count_ptr: int | None = None,

@@ -29,10 +29,65 @@ struct SearchParams {
   // fused exchange of the sharded corpus: besides (or instead of) out_ids/out_dist the top-k of
   // query qi is stored into every destination's [n_slots][B][k] gather buffer at slot `slot`;
   // destinations are peer GPUs' buffers mapped over NVLink (plain st.global on peer pointers).
+  // per-row filter verdicts (bit id = the row passes): applied to the final beam BEFORE the trim to k,
+  // like the filter bytecode of hnsw_knn (hnsw.rs:943-947, 997-1006); nullptr = no filter
+  const uint32_t* filter_mask;
   uint32_t n_dest, slot;
   uint32_t* dest_ids[COZO_GPU_MAX_PEERS];
   float* dest_dist[COZO_GPU_MAX_PEERS];
 };
+
+
+// hnsw_knn's tail (hnsw.rs:943-956, 997-1006) for the query of this warp: walk the beam nearest first, drop
+// `dist > radius` and rows the filter rejects, keep the first k, pad the rest.  Without a filter the kept
+// entries are a prefix of the sorted array.  Returns the number of results.
+__device__ __forceinline__ uint32_t emit_results(const SearchParams& p, const WarpCtx& w, uint32_t qi, int lane,
+                                                 bool searched) {
+  auto store = [&](uint32_t i, uint32_t oid, float od) {
+    if (p.out_ids) {
+      p.out_ids[(size_t)qi * p.k + i] = oid;
+      p.out_dist[(size_t)qi * p.k + i] = od;
+    }
+    const size_t at = ((size_t)p.slot * p.B + qi) * p.k + i;
+    for (uint32_t d = 0; d < p.n_dest; ++d) {  // the all-gather, fused into the epilogue
+      p.dest_ids[d][at] = oid;
+      p.dest_dist[d][at] = od;
+    }
+  };
+  uint32_t found = 0;
+  if (searched && !p.filter_mask) {
+    found = w.len < p.k ? w.len : p.k;
+    if (p.has_radius) {
+      uint32_t c = 0;
+      for (uint32_t base_i = 0; base_i < found; base_i += 32) {
+        uint32_t i = base_i + lane;
+        bool in = i < found && !((double)w.fd[i] > p.radius);
+        c += __popc(__ballot_sync(0xffffffffu, in));
+      }
+      found = c;
+    }
+    for (uint32_t i = lane; i < found; i += 32) store(i, w.fi[i] & IDMASK, w.fd[i]);
+  } else if (searched) {
+    for (uint32_t base_i = 0; base_i < w.len && found < p.k; base_i += 32) {
+      const uint32_t i = base_i + lane;
+      bool ok = i < w.len;
+      uint32_t id = 0;
+      float d = 0.f;
+      if (ok) {
+        id = w.fi[i] & IDMASK;
+        d = w.fd[i];
+        ok = ((p.filter_mask[id >> 5] >> (id & 31)) & 1u) && !(p.has_radius && (double)d > p.radius);
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+      const uint32_t pos = found + __popc(bal & ((1u << lane) - 1));
+      if (ok && pos < p.k) store(pos, id, d);
+      found += __popc(bal);
+    }
+    if (found > p.k) found = p.k;
+  }
+  for (uint32_t i = found + lane; i < p.k; i += 32) store(i, NONE, INFINITY);
+  return found;
+}
 
 // One warp per query, persistent CTAs pulling query indices from a counter.
 // MINB = resident CTAs per SM the register allocation is capped for (4 warps per CTA).
@@ -93,32 +148,8 @@ __global__ void __launch_bounds__(128, MINB) hnsw_search_kernel(HnswDev g, Searc
       for (uint32_t lvl = g.top_level; lvl >= 1; --lvl)  // hnsw.rs:919-929
         search_level<NV, METRIC, BULK>(g, w, q, qnorm, 1, lvl, lane);
       search_level<NV, METRIC, BULK>(g, w, q, qnorm, p.ef, 0, lane);  // hnsw.rs:930-938
-      // trim to k, drop dist > radius, nearest first (hnsw.rs:943-956,1005-1006)
-      found = w.len < p.k ? w.len : p.k;
-      if (p.has_radius) {
-        uint32_t c = 0;
-        for (uint32_t base_i = 0; base_i < found; base_i += 32) {
-          uint32_t i = base_i + lane;
-          bool in = i < found && !((double)w.fd[i] > p.radius);
-          c += __popc(__ballot_sync(0xffffffffu, in));
-        }
-        found = c;
-      }
     }
-    for (uint32_t i = lane; i < p.k; i += 32) {
-      const bool in = i < found;
-      const uint32_t oid = in ? (w.fi[i] & IDMASK) : NONE;
-      const float od = in ? w.fd[i] : INFINITY;
-      if (p.out_ids) {
-        p.out_ids[(size_t)qi * p.k + i] = oid;
-        p.out_dist[(size_t)qi * p.k + i] = od;
-      }
-      const size_t at = ((size_t)p.slot * p.B + qi) * p.k + i;
-      for (uint32_t d = 0; d < p.n_dest; ++d) {  // the all-gather, fused into the epilogue
-        p.dest_ids[d][at] = oid;
-        p.dest_dist[d][at] = od;
-      }
-    }
+    found = emit_results(p, w, qi, lane, g.entry != NONE);
     if (lane == 0) {
       if (p.out_count) p.out_count[qi] = found;
       if (p.qstats) {
@@ -195,34 +226,9 @@ __global__ void __launch_bounds__(128, 4) hnsw_search_coop_kernel(HnswDev g, Sea
       for (uint32_t lvl = g.top_level; lvl >= 1; --lvl)
         coop_search_level<NV, METRIC>(g, w, cs, q, qnorm, 1, lvl, lane, warp);
       coop_search_level<NV, METRIC>(g, w, cs, q, qnorm, p.ef, 0, lane, warp);
-      if (warp == 0) {
-        found = w.len < p.k ? w.len : p.k;
-        if (p.has_radius) {
-          uint32_t c = 0;
-          for (uint32_t base_i = 0; base_i < found; base_i += 32) {
-            uint32_t i = base_i + lane;
-            bool in = i < found && !((double)w.fd[i] > p.radius);
-            c += __popc(__ballot_sync(0xffffffffu, in));
-          }
-          found = c;
-        }
-      }
     }
     if (warp == 0) {
-      for (uint32_t i = lane; i < p.k; i += 32) {
-        const bool in = i < found;
-        const uint32_t oid = in ? (w.fi[i] & IDMASK) : NONE;
-        const float od = in ? w.fd[i] : INFINITY;
-        if (p.out_ids) {
-          p.out_ids[(size_t)qi * p.k + i] = oid;
-          p.out_dist[(size_t)qi * p.k + i] = od;
-        }
-        const size_t at = ((size_t)p.slot * p.B + qi) * p.k + i;
-        for (uint32_t d = 0; d < p.n_dest; ++d) {
-          p.dest_ids[d][at] = oid;
-          p.dest_dist[d][at] = od;
-        }
-      }
+      found = emit_results(p, w, qi, lane, g.entry != NONE);
       if (lane == 0) {
         if (p.out_count) p.out_count[qi] = found;
         if (p.qstats) reinterpret_cast<uint4*>(p.qstats)[qi] = make_uint4(w.dist_evals, w.nodes_expanded, w.nbr_reads, 0);
@@ -393,6 +399,7 @@ static void free_ws(HnswWorkspace* ws) {
   if (ws->dist) cudaFree(ws->dist);
   if (ws->count) cudaFree(ws->count);
   if (ws->qstats) cudaFree(ws->qstats);
+  if (ws->mask) cudaFree(ws->mask);
   if (ws->e0) cudaEventDestroy(ws->e0);
   if (ws->e1) cudaEventDestroy(ws->e1);
   if (ws->stream) cudaStreamDestroy(ws->stream);
@@ -401,7 +408,7 @@ static void free_ws(HnswWorkspace* ws) {
 
 int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, uint32_t B, uint32_t k, uint32_t ef,
                        double radius, uint32_t* d_ids, float* d_dist, uint32_t* d_count, uint32_t* d_qstats,
-                       cudaStream_t stream, const ScatterDest* scatter) {
+                       cudaStream_t stream, const ScatterDest* scatter, const uint32_t* d_filter_mask) {
   const DeviceInfo& di = device_info();
   const HnswDev& g = h->dev;
   if (B == 0) return 0;
@@ -497,6 +504,7 @@ int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, ui
   p.vlog = ws->vlog;
   p.logcap = logcap;
   p.ns = ns;
+  p.filter_mask = d_filter_mask;
   p.n_dest = 0;
   p.slot = 0;
   if (scatter) {
@@ -686,7 +694,8 @@ static int check_search_args(cozo_gpu_hnsw_t* h, uint32_t k, uint32_t ef) {
 
 static int search_dev_impl(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k, uint32_t ef,
                            double radius, uint32_t* out_ids_dev, float* out_dist_dev, uint32_t* out_count_dev,
-                           uint32_t* per_query_stats_dev, void* stream, const ScatterDest* scatter) {
+                           uint32_t* per_query_stats_dev, void* stream, const ScatterDest* scatter,
+                           const uint32_t* filter_mask_dev = nullptr) {
   int rc = check_search_args(h, k, ef);
   if (rc) return rc;
   if (B && !queries_dev) return set_error(COZO_GPU_EINVAL, "null buffer");
@@ -695,7 +704,7 @@ static int search_dev_impl(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_
   HnswWorkspace* ws = hnsw_acquire_ws(h);
   if (!ws) return COZO_GPU_ECUDA;
   rc = hnsw_launch_search(h, ws, queries_dev, B, k, ef, radius, out_ids_dev, out_dist_dev, out_count_dev,
-                          per_query_stats_dev, (cudaStream_t)stream, scatter);
+                          per_query_stats_dev, (cudaStream_t)stream, scatter, filter_mask_dev);
   // The workspace (visited bitmaps) stays in use until the kernel ends: hand it
   // back to the pool from a host callback ordered after the kernel on `stream`,
   // which keeps this call asynchronous.
@@ -749,9 +758,9 @@ extern "C" int cozo_gpu_hnsw_search_scatter_dev(cozo_gpu_hnsw_t* h, const float*
   return search_dev_impl(h, queries_dev, B, k, ef, radius, nullptr, nullptr, nullptr, per_query_stats_dev, stream, &sc);
 }
 
-extern "C" int cozo_gpu_hnsw_search(cozo_gpu_hnsw_t* h, const float* queries, uint32_t B, uint32_t k, uint32_t ef,
-                                    double radius, uint32_t* out_ids, float* out_dist, uint32_t* out_count,
-                                    CozoGpuSearchStats* stats) {
+static int search_host_impl(cozo_gpu_hnsw_t* h, const float* queries, uint32_t B, uint32_t k, uint32_t ef, double radius,
+                            const uint32_t* row_mask, uint32_t* out_ids, float* out_dist, uint32_t* out_count,
+                            CozoGpuSearchStats* stats) {
   int rc = check_search_args(h, k, ef);
   if (rc) return rc;
   if (B && (!queries || !out_ids || !out_dist)) return set_error(COZO_GPU_EINVAL, "null buffer");
@@ -798,9 +807,21 @@ extern "C" int cozo_gpu_hnsw_search(cozo_gpu_hnsw_t* h, const float* queries, ui
     ws->out_k = kk;
   }
   cudaStream_t st = ws->stream;
+  if (row_mask) {
+    const size_t words = ((size_t)h->dev.n + 31) / 32;
+    if (ws->mask_words < words) {
+      if (ws->mask) cudaFree(ws->mask);
+      ws->mask = nullptr;
+      ws->mask_words = 0;
+      S_CUDA(cudaMalloc(&ws->mask, std::max<size_t>(words, 1) * 4));
+      ws->mask_words = words;
+    }
+    S_CUDA(cudaMemcpyAsync(ws->mask, row_mask, words * 4, cudaMemcpyHostToDevice, st));
+  }
   S_CUDA(cudaMemcpyAsync(ws->q, queries, qf * 4, cudaMemcpyHostToDevice, st));
   S_CUDA(cudaEventRecord(ws->e0, st));
-  rc = hnsw_launch_search(h, ws, ws->q, B, k, ef, radius, ws->ids, ws->dist, ws->count, ws->qstats, st, nullptr);
+  rc = hnsw_launch_search(h, ws, ws->q, B, k, ef, radius, ws->ids, ws->dist, ws->count, ws->qstats, st, nullptr,
+                          row_mask ? ws->mask : nullptr);
   if (rc) return done(rc);
   S_CUDA(cudaEventRecord(ws->e1, st));
   S_CUDA(cudaMemcpyAsync(out_ids, ws->ids, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
@@ -825,6 +846,28 @@ extern "C" int cozo_gpu_hnsw_search(cozo_gpu_hnsw_t* h, const float* queries, ui
   }
 #undef S_CUDA
   return done(0);
+}
+
+extern "C" int cozo_gpu_hnsw_search(cozo_gpu_hnsw_t* h, const float* queries, uint32_t B, uint32_t k, uint32_t ef,
+                                    double radius, uint32_t* out_ids, float* out_dist, uint32_t* out_count,
+                                    CozoGpuSearchStats* stats) {
+  return search_host_impl(h, queries, B, k, ef, radius, nullptr, out_ids, out_dist, out_count, stats);
+}
+
+extern "C" int cozo_gpu_hnsw_search_filtered(cozo_gpu_hnsw_t* h, const float* queries, uint32_t B, uint32_t k,
+                                             uint32_t ef, double radius, const uint32_t* row_mask, uint32_t* out_ids,
+                                             float* out_dist, uint32_t* out_count, CozoGpuSearchStats* stats) {
+  if (h && h->dev.n && !row_mask) return set_error(COZO_GPU_EINVAL, "null row mask");
+  return search_host_impl(h, queries, B, k, ef, radius, row_mask, out_ids, out_dist, out_count, stats);
+}
+
+extern "C" int cozo_gpu_hnsw_search_filtered_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k,
+                                                 uint32_t ef, double radius, const uint32_t* row_mask_dev,
+                                                 uint32_t* out_ids_dev, float* out_dist_dev, uint32_t* out_count_dev,
+                                                 uint32_t* per_query_stats_dev, void* stream) {
+  if (!row_mask_dev) return set_error(COZO_GPU_EINVAL, "null row mask");
+  return search_dev_impl(h, queries_dev, B, k, ef, radius, out_ids_dev, out_dist_dev, out_count_dev,
+                         per_query_stats_dev, stream, nullptr, row_mask_dev);
 }
 
 extern "C" int cozo_gpu_hnsw_info(cozo_gpu_hnsw_t* h, uint32_t* n_vectors, uint32_t* dim, uint32_t* n_levels,

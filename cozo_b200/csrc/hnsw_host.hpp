@@ -22,6 +22,8 @@ struct HnswWorkspace {
   uint32_t* count = nullptr;
   uint32_t* qstats = nullptr;
   size_t out_rows = 0, out_k = 0;
+  uint32_t* mask = nullptr;  // row filter verdicts of the host-pointer call
+  size_t mask_words = 0;
   // pinned mirrors
   float* h_q = nullptr;
   size_t h_q_floats = 0;
@@ -70,7 +72,7 @@ struct ScatterDest {
 };
 int hnsw_launch_search(cozo_gpu_hnsw* h, HnswWorkspace* ws, const float* d_q, uint32_t B, uint32_t k, uint32_t ef,
                        double radius, uint32_t* d_ids, float* d_dist, uint32_t* d_count, uint32_t* d_qstats,
-                       cudaStream_t stream, const ScatterDest* scatter);
+                       cudaStream_t stream, const ScatterDest* scatter, const uint32_t* d_filter_mask = nullptr);
 HnswWorkspace* hnsw_acquire_ws(cozo_gpu_hnsw* h);
 void hnsw_release_ws(cozo_gpu_hnsw* h, HnswWorkspace* ws);
 int hnsw_ws_reserve(HnswWorkspace* ws, size_t vis_words, size_t vlog_words, cudaStream_t stream);

@@ -38,7 +38,17 @@ struct Poison {
 // ---- RegularTempStore (runtime/temp_store.rs:27-29,58-60) --------------------------
 struct RegularTempStore {
   std::map<Tuple, bool, TupleLess> inner;
-  void put(Tuple t) { inner.emplace(std::move(t), false); }
+  void put(Tuple t) { inner.emplace(std::move(t), false); }  // RegularTempStore::put (temp_store.rs:58-60)
+  // Bulk fill for rules that emit one row per node: rows arrive in ascending key order (the glue walks its
+  // key -> id dictionary in order), so every insert is an append at the end of the tree.  MEASURED on this
+  // std::map twin (_cozo_host.bench_tempstore_fill, 2M rows): no gain — 1.3 s with put, 1.7 s through the
+  // ordered walk; the time goes into materialising the tuples, not into the tree.  Kept for the record and not
+  // used by the rules; whether Rust's BTreeMap bulk build (`from_iter` over a sorted iterator) does better is
+  // unverified.
+  template <class RowFn>  // row(i) -> Tuple for i in [0,n), ascending keys
+  void put_sorted_bulk(size_t n, RowFn row) {
+    for (size_t i = 0; i < n; ++i) inner.emplace_hint(inner.end(), row(i), false);  // a wrong hint only costs time
+  }
   std::vector<Tuple> rows() const {
     std::vector<Tuple> r;
     for (auto& kv : inner) r.push_back(kv.first);

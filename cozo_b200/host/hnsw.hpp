@@ -73,7 +73,10 @@ struct KvRelation {
     r.kv.reserve(rel.rows.size());
     for (auto& row : rel.rows)
       r.kv.emplace_back(memcmp_codec::encode_as_key(row.first, id), msgpack_codec::encode_vals(row.second, r.n_keys, id));
-    std::sort(r.kv.begin(), r.kv.end());  // byte order == value order, so this is a no-op check in practice
+    // storage order = byte order of the memcmp keys.  For Null/Bool/Num/Str/Bytes/List keys it equals DataValue
+    // order; for Vec keys it does not (VEC_TAG 0x04 sorts before numbers, elements are raw BE bits) — the byte-level
+    // planner (plan_kv_bytes) follows storage order like the reference's scans do (hnsw.rs:891-899)
+    std::sort(r.kv.begin(), r.kv.end());
     return r;
   }
   const std::string* get_val_bytes(const std::string& k) const {
@@ -448,6 +451,14 @@ struct StagedHnswIndex {
              &n_rows_dropped_ignored = pl.n_rows_dropped_ignored;
     if (mf.dtype_f64)
       throw CozoError("gpu::unsupported", "F64 vector indexes are outside the device envelope (f32 only)");
+    // This planner orders rows and compound keys by DataValue order.  Storage (and the reference's entry-point
+    // scan, hnsw.rs:891-899) orders them by memcmp bytes; the two agree for every key type except Vec, whose tag
+    // sorts before numbers and whose elements are raw big-endian bits.  Relations keyed by vectors go through
+    // stage_kv / plan_kv_bytes, which works on the stored bytes; refuse them here instead of mis-ordering.
+    for (const Tuple& t : idx_rows)
+      for (size_t c = 1; c < t.size() && c < 2 * K + 5; ++c)
+        if (t[c].kind == DataValue::Vec)
+          throw CozoError("gpu::unsupported", "vector-typed key columns: stage this index from KV bytes (stage_kv)");
     std::sort(idx_rows.begin(), idx_rows.end(), TupleLess());
     // dense ids = compound keys of the layer-0 self-loop rows, in key order
     std::map<CompoundKey, uint32_t, CompoundKeyLess> ids;
@@ -664,6 +675,7 @@ struct StagedHnswIndex {
   // base relation (`rebuilt` counts those).
   std::map<CompoundKey, uint32_t, CompoundKeyLess> key_ids;  // compound key -> dense id (lazily rebuilt)
   std::vector<uint8_t> live;                                  // host mirror of the device's live flags
+  bool is_live(uint32_t id) const { return live.size() != keys.size() || live[id] != 0; }
   uint64_t n_put_unchanged = 0, n_put_updated = 0, n_put_appended = 0, n_removed = 0, n_rebuilt = 0;
 
   void sync_dictionary() {
@@ -886,6 +898,10 @@ struct HnswSearch {
   bool bind_field = false, bind_field_idx = false, bind_distance = false, bind_vector = false;
   std::optional<double> radius;
   std::function<bool(const Tuple&)> filter;  // compiled filter bytecode stand-in (hnsw.rs:997-1001)
+  // whether the filter expression reads the bound distance (the only binding that depends on the query).
+  // If it does not, the verdict is a property of the indexed row: the glue evaluates the bytecode once per
+  // row, ships a bit mask, and the kernel trims to k after filtering (cozo_gpu_hnsw_search_filtered).
+  bool filter_reads_distance = true;
 
   void validate() const {  // SearchInput::normalize_hnsw (program.rs:1341-1569)
     if (k == 0) throw CozoError("parser::expected_positive_int_for_hnsw_k", "Expected positive integer for `k`");
@@ -907,35 +923,55 @@ inline std::vector<std::vector<Tuple>> hnsw_knn_batch(const std::vector<const st
     if (queries[i]->size() != dim) throw CozoError("", "query vector dimension mismatch");  // hnsw.rs:876-878
     std::copy(queries[i]->begin(), queries[i]->end(), q.begin() + (size_t)i * dim);
   }
-  // with a filter the trim to k happens after filtering (hnsw.rs:943-947, 1005-1006)
-  const uint32_t k_dev = config.filter ? (uint32_t)config.ef : (uint32_t)std::min(config.k, config.ef);
+  const RelationHandle& base = *config.base_handle;
+  // candidate row of an indexed vector: base row ++ bindings in the order of HnswSearch::all_bindings
+  // (hnsw.rs:958-995, program.rs:1016-1025)
+  auto assemble = [&](uint32_t id, const DataValue& distance) {
+    const CompoundKey& ck = ix.keys[id];
+    const Tuple* row = base.get(std::get<0>(ck));
+    if (!row) throw CozoError("", "corrupted index");  // hnsw.rs:958-961
+    Tuple cand = *row;
+    const size_t fld = std::get<1>(ck);
+    const int32_t sub = std::get<2>(ck);
+    if (config.bind_field)  // hnsw.rs:964-974
+      cand.push_back(DataValue::from_str(fld < base.keys.size() ? base.keys[fld] : base.non_keys[fld - base.keys.size()]));
+    if (config.bind_field_idx) cand.push_back(sub < 0 ? DataValue::null() : DataValue::from_int(sub));  // 975-981
+    if (config.bind_distance) cand.push_back(distance);  // 982-984
+    if (config.bind_vector) {  // 985-995
+      if (sub < 0) {
+        cand.push_back((*row)[fld]);
+      } else {
+        if ((*row)[fld].kind != DataValue::List) throw CozoError("", "corrupted index value");
+        cand.push_back((*row)[fld].list[(size_t)sub]);
+      }
+    }
+    return cand;
+  };
+  // with a filter the trim to k happens after filtering (hnsw.rs:943-947, 1005-1006): either inside the kernel
+  // (per-row verdicts as a bit mask) or, when the filter reads the distance, on the host over all ef candidates
+  const bool device_filter = config.filter && !config.filter_reads_distance;
+  const uint32_t k_dev = (config.filter && !device_filter) ? (uint32_t)config.ef : (uint32_t)std::min(config.k, config.ef);
   std::vector<uint32_t> ids((size_t)B * k_dev), count(B);
   std::vector<float> dist((size_t)B * k_dev);
-  gpu_check(cozo_gpu_hnsw_search(ix.h, q.data(), B, k_dev, (uint32_t)config.ef, config.radius ? *config.radius : -1.0,
-                                 ids.data(), dist.data(), count.data(), stats));
-  const RelationHandle& base = *config.base_handle;
+  if (device_filter) {
+    const size_t n = ix.keys.size();
+    std::vector<uint32_t> mask((n + 31) / 32 + 1, 0u);
+    for (size_t id = 0; id < n; ++id)
+      if (ix.is_live((uint32_t)id) && base.get(std::get<0>(ix.keys[id])) &&  // removed rows never come back from the device
+          config.filter(assemble((uint32_t)id, DataValue::null())))
+        mask[id >> 5] |= 1u << (id & 31);
+    gpu_check(cozo_gpu_hnsw_search_filtered(ix.h, q.data(), B, k_dev, (uint32_t)config.ef,
+                                            config.radius ? *config.radius : -1.0, mask.data(), ids.data(), dist.data(),
+                                            count.data(), stats));
+  } else {
+    gpu_check(cozo_gpu_hnsw_search(ix.h, q.data(), B, k_dev, (uint32_t)config.ef, config.radius ? *config.radius : -1.0,
+                                   ids.data(), dist.data(), count.data(), stats));
+  }
   std::vector<std::vector<Tuple>> out(B);
   for (uint32_t i = 0; i < B; ++i) {
     for (uint32_t j = 0; j < count[i]; ++j) {
-      const CompoundKey& ck = ix.keys[ids[(size_t)i * k_dev + j]];
-      const Tuple* row = base.get(std::get<0>(ck));
-      if (!row) throw CozoError("", "corrupted index");  // hnsw.rs:958-961
-      Tuple cand = *row;
-      const size_t fld = std::get<1>(ck);
-      const int32_t sub = std::get<2>(ck);
-      if (config.bind_field)  // hnsw.rs:964-974
-        cand.push_back(DataValue::from_str(fld < base.keys.size() ? base.keys[fld] : base.non_keys[fld - base.keys.size()]));
-      if (config.bind_field_idx) cand.push_back(sub < 0 ? DataValue::null() : DataValue::from_int(sub));  // 975-981
-      if (config.bind_distance) cand.push_back(DataValue::from_float((double)dist[(size_t)i * k_dev + j]));  // 982-984
-      if (config.bind_vector) {  // 985-995
-        if (sub < 0) {
-          cand.push_back((*row)[fld]);
-        } else {
-          if ((*row)[fld].kind != DataValue::List) throw CozoError("", "corrupted index value");
-          cand.push_back((*row)[fld].list[(size_t)sub]);
-        }
-      }
-      if (config.filter && !config.filter(cand)) continue;  // hnsw.rs:997-1001
+      Tuple cand = assemble(ids[(size_t)i * k_dev + j], DataValue::from_float((double)dist[(size_t)i * k_dev + j]));
+      if (config.filter && !device_filter && !config.filter(cand)) continue;  // hnsw.rs:997-1001
       out[i].push_back(std::move(cand));
     }
     if (out[i].size() > config.k) out[i].resize(config.k);  // hnsw.rs:1006

@@ -184,7 +184,7 @@ inline size_t decode_datavalue(const uint8_t* p, size_t n, DataValue& out) {
       const uint64_t len = get_u64_be(p + 2);
       const size_t esz = t == VEC_F32 ? 4 : 8;
       if (t != VEC_F32 && t != VEC_F64) throw CozoError("", "corrupt vector tag");
-      if (n < 10 + len * esz) throw CozoError("", "truncated vector");
+      if (len > (n - 10) / esz) throw CozoError("", "truncated vector");  // overflow-safe: len is untrusted
       std::vector<float> v(len);
       for (uint64_t i = 0; i < len; ++i) {
         const uint8_t* e = p + 10 + i * esz;
@@ -247,9 +247,10 @@ inline size_t skip_datavalue(const uint8_t* p, size_t n) {
     case VEC_TAG: {
       if (n < 10) throw CozoError("", "truncated vector");
       if (p[1] != VEC_F32 && p[1] != VEC_F64) throw CozoError("", "corrupt vector tag");
-      const size_t total = 10 + (size_t)get_u64_be(p + 2) * (p[1] == VEC_F32 ? 4 : 8);
-      if (n < total) throw CozoError("", "truncated vector");
-      return total;
+      const uint64_t len = get_u64_be(p + 2);
+      const size_t esz = p[1] == VEC_F32 ? 4 : 8;
+      if (len > (n - 10) / esz) throw CozoError("", "truncated vector");  // overflow-safe: len is untrusted
+      return 10 + (size_t)len * esz;
     }
     default: throw CozoError("", "unsupported memcmp tag " + std::to_string((int)p[0]));
   }

@@ -218,7 +218,7 @@ struct PyHnswSearchRA {
   std::shared_ptr<PyHnswIndex> index;
   PyHnswSearchRA(std::shared_ptr<PyRelation> b, std::shared_ptr<PyHnswIndex> ix, size_t k, size_t ef, py::object radius,
                  bool bind_field, bool bind_field_idx, bool bind_distance, bool bind_vector, py::object filter,
-                 size_t bind_idx)
+                 size_t bind_idx, bool filter_reads_distance)
       : base(std::move(b)), index(std::move(ix)) {
     ra.hnsw_search.base_handle = &base->rel;
     ra.hnsw_search.index = &index->ix;
@@ -234,6 +234,7 @@ struct PyHnswSearchRA {
       ra.hnsw_search.filter = [f](const Tuple& t) { return f(from_tuple(t)).cast<bool>(); };
     }
     ra.bind_idx = bind_idx;
+    ra.hnsw_search.filter_reads_distance = filter_reads_distance;
   }
   py::list iter(py::handle parent) { return from_rows(ra.iter(to_rows(parent))); }
   py::dict stats() const {
@@ -282,10 +283,11 @@ PYBIND11_MODULE(_cozo_host, m) {
       .def("info", &PyHnswIndex::info);
   py::class_<PyHnswSearchRA>(m, "HnswSearchRA")
       .def(py::init<std::shared_ptr<PyRelation>, std::shared_ptr<PyHnswIndex>, size_t, size_t, py::object, bool, bool,
-                    bool, bool, py::object, size_t>(),
+                    bool, bool, py::object, size_t, bool>(),
            py::arg("base"), py::arg("index"), py::arg("k"), py::arg("ef"), py::arg("radius") = py::none(),
            py::arg("bind_field") = false, py::arg("bind_field_idx") = false, py::arg("bind_distance") = false,
-           py::arg("bind_vector") = false, py::arg("filter") = py::none(), py::arg("bind_idx") = 0)
+           py::arg("bind_vector") = false, py::arg("filter") = py::none(), py::arg("bind_idx") = 0,
+           py::arg("filter_reads_distance") = true)
       .def("iter", &PyHnswSearchRA::iter)
       .def("stats", &PyHnswSearchRA::stats);
   m.def("cmp", [](py::handle a, py::handle b) { return cmp(to_dv(a), to_dv(b)); });
@@ -360,6 +362,41 @@ PYBIND11_MODULE(_cozo_host, m) {
     return plan_to_py(bytes_level ? StagedHnswIndex::plan_kv_bytes(b, i, m) : StagedHnswIndex::plan_kv_tuples(b, i, m));
   }, py::arg("base_kv"), py::arg("base_id"), py::arg("n_keys"), py::arg("idx_kv"), py::arg("idx_id"), py::arg("mf"),
      py::arg("bytes_level") = true);
+  // FixedRule output: RegularTempStore::put per row vs the sorted bulk fill (n rows (string key, score))
+  m.def("bench_tempstore_fill", [](uint32_t n) {
+    std::vector<DataValue> keys;
+    keys.reserve(n);
+    char buf[32];
+    for (uint32_t i = 0; i < n; ++i) {
+      snprintf(buf, sizeof buf, "node%010u", (unsigned)((uint64_t)i * 2654435761u % 4000000007u));
+      keys.push_back(DataValue::from_str(buf));
+    }
+    std::map<DataValue, uint32_t, DataValueLess> dict;  // the glue's key -> id dictionary
+    for (uint32_t i = 0; i < n; ++i) dict.emplace(keys[i], i);
+    auto t0 = std::chrono::steady_clock::now();
+    RegularTempStore a;
+    for (uint32_t i = 0; i < n; ++i) a.put({keys[i], DataValue::from_float(0.5 * i)});
+    auto t1 = std::chrono::steady_clock::now();
+    RegularTempStore b;
+    std::vector<uint32_t> order;
+    order.reserve(n);
+    for (auto& kv : dict) order.push_back(kv.second);
+    b.put_sorted_bulk(order.size(), [&](size_t i) { return Tuple{keys[order[i]], DataValue::from_float(0.5 * order[i])}; });
+    auto t2 = std::chrono::steady_clock::now();
+    bool same = a.inner.size() == b.inner.size();
+    if (same) {
+      auto ia = a.inner.begin();
+      auto ib = b.inner.begin();
+      for (; ia != a.inner.end(); ++ia, ++ib)
+        if (cmp_tuple(ia->first, ib->first) != 0) same = false;
+    }
+    py::dict d;
+    d["rows"] = n;
+    d["put_s"] = std::chrono::duration<double>(t1 - t0).count();
+    d["bulk_s"] = std::chrono::duration<double>(t2 - t1).count();
+    d["identical"] = same;
+    return d;
+  });
   // throughput of the two KV planners on a synthetic index (n vectors, `deg` neighbours each, int keys)
   m.def("bench_stage_kv", [](uint32_t n, uint32_t dim, uint32_t deg, bool bytes_level) {
     RelationHandle base;

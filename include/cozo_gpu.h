@@ -124,6 +124,19 @@ int cozo_gpu_hnsw_search_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint3
                              double radius, uint32_t* out_ids_dev, float* out_dist_dev, uint32_t* out_count_dev,
                              uint32_t* per_query_stats_dev, void* stream);
 
+/* hnsw_knn with a `filter` (hnsw.rs:943-947, 997-1006): the beam is NOT trimmed to k before the filter; rows
+ * are dropped where the filter bytecode is false and only then the first k are kept.  The host evaluates the
+ * filter once per indexed row (possible whenever the expression does not read the bound distance) and passes
+ * the verdicts as a bit mask: bit (id & 31) of word id >> 5 set = row `id` passes; [ceil(n_vectors/32)] words.
+ * The trim happens inside the kernel, so only k results per query travel back. */
+int cozo_gpu_hnsw_search_filtered(cozo_gpu_hnsw_t* h, const float* queries, uint32_t B, uint32_t k, uint32_t ef,
+                                  double radius, const uint32_t* row_mask, uint32_t* out_ids, float* out_dist,
+                                  uint32_t* out_count, CozoGpuSearchStats* stats);
+int cozo_gpu_hnsw_search_filtered_dev(cozo_gpu_hnsw_t* h, const float* queries_dev, uint32_t B, uint32_t k,
+                                      uint32_t ef, double radius, const uint32_t* row_mask_dev, uint32_t* out_ids_dev,
+                                      float* out_dist_dev, uint32_t* out_count_dev, uint32_t* per_query_stats_dev,
+                                      void* stream);
+
 /* Sharded corpus, fused search + exchange: the search kernel stores the top-k of
  * every query straight into the [n_slots][B][k] gather buffers of all `n_dest` destinations at
  * slot `slot` (this rank) — peer GPUs' buffers mapped into this process over NVLink (CUDA IPC /

@@ -46,10 +46,21 @@ fn check(rc: std::os::raw::c_int) -> Result<()> {
 pub(crate) struct StagedIndex {
     h: *mut CozoGpuHnsw,
     keys: Vec<CompoundKey>,
-    /// Relation ids + a write counter: a mutation of either relation through `hnsw_put` /
-    /// `hnsw_remove` (runtime/hnsw.rs:694-867) bumps the counter held in the handle's metadata;
-    /// a mismatch re-stages (INTEGRATION.md "staleness").
-    stamp: (u64, u64, u64),
+    /// (base relation id, index relation id) the copy was staged from.
+    stamp: (u64, u64),
+}
+
+/// The reference keeps no index version counter, so the device copy is dropped AT the mutation sites
+/// (one added line each, INTEGRATION.md §2 lists them):
+///   hnsw_put    <- query/stored.rs:332, :630 and runtime/relation.rs:1177 (create_hnsw_index bulk insert)
+///   hnsw_remove <- query/stored.rs:995-997
+///   index drop  <- runtime/relation.rs:1383 (`hnsw_indices.remove`)
+/// each calls `gpu_index_invalidate(idx_handle.id)` before touching the relation.  The next search
+/// re-stages (or, for appends and in-place updates, the glue can call cozo_gpu_hnsw_insert / _update /
+/// _remove instead — `StagedHnswIndex::put_rows` / `remove_rows` in the C++ twin show the exact rules).
+/// A staged copy is only handed to readers whose transaction started after the staging.
+pub(crate) fn gpu_index_invalidate(idx_rel_id: crate::runtime::relation::RelationId) {
+    STAGED.lock().unwrap().remove(&idx_rel_id.0);
 }
 
 unsafe impl Send for StagedIndex {}
@@ -73,7 +84,8 @@ impl StagedIndex {
         idx: &RelationHandle,
         mf: &HnswIndexManifest,
     ) -> Result<Arc<StagedIndex>> {
-        let stamp = (base.id.0, idx.id.0, idx.gpu_write_epoch());
+        crate::fixed_rule::algos::gpu::ensure_device()?; // no CPU fallback: surfaces the init error
+        let stamp = (base.id.0, idx.id.0);
         let mut map = STAGED.lock().unwrap();
         if let Some(s) = map.get(&idx.id.0) {
             if s.stamp == stamp {
@@ -90,7 +102,7 @@ impl StagedIndex {
         base: &RelationHandle,
         idx: &RelationHandle,
         mf: &HnswIndexManifest,
-        stamp: (u64, u64, u64),
+        stamp: (u64, u64),
     ) -> Result<Self> {
         if mf.dtype != VecElementType::F32 {
             bail!("gpu-b200: F64 vector indexes are outside the device envelope");
@@ -237,59 +249,56 @@ impl<'a> SessionTx<'a> {
             }
         }
         let staged = StagedIndex::get_or_stage(self, &config.base_handle, &config.idx_handle, &config.manifest)?;
-        // with a filter the reference keeps all ef results and filters before truncating to k
-        // (hnsw.rs:942-946, 1001-1008): ask the device for ef
-        let k_dev = if config.filter.is_some() { config.ef } else { config.k.min(config.ef) };
+        // With a filter the reference keeps all ef results and filters before truncating to k
+        // (hnsw.rs:942-946, 1001-1008).  If the bytecode never reads the bound distance, its verdict is a
+        // property of the indexed row: evaluate it once per row, ship the verdicts as a bit mask and let the
+        // kernel trim to k after filtering (cozo_gpu_hnsw_search_filtered).  Otherwise ask for all ef
+        // candidates and filter here.
+        let nk = config.base_handle.metadata.keys.len();
+        let dist_pos = self.distance_binding_pos(config);
+        let device_filter = match (filter_bytecode, dist_pos) {
+            (Some((code, _)), Some(p)) => !code.iter().any(|bc| matches!(bc, Bytecode::Binding { tuple_pos: Some(tp), .. } if *tp == p)),
+            (Some(_), None) => true,
+            (None, _) => false,
+        };
+        let k_dev = if filter_bytecode.is_some() && !device_filter { config.ef } else { config.k.min(config.ef) };
         let b = qs.len();
         let mut ids = vec![COZO_GPU_NONE; b * k_dev];
         let mut dist = vec![0f32; b * k_dev];
         let mut count = vec![0u32; b];
         let mut stats = CozoGpuSearchStats::default();
-        check(unsafe {
-            cozo_gpu_hnsw_search(
-                staged.h, flat.as_ptr(), b as u32, k_dev as u32, config.ef as u32,
-                config.radius.unwrap_or(-1.0), // < 0: no radius
-                ids.as_mut_ptr(), dist.as_mut_ptr(), count.as_mut_ptr(), &mut stats,
-            )
-        })?;
-        let nk = config.base_handle.metadata.keys.len();
+        if device_filter {
+            let (code, span) = filter_bytecode.as_ref().unwrap();
+            let mut mask = vec![0u32; (staged.keys.len() + 31) / 32 + 1];
+            for (id, key) in staged.keys.iter().enumerate() {
+                let cand = self.assemble_candidate(config, key, nk, DataValue::Null)?; // distance slot unused by the filter
+                if eval_bytecode_pred(code, &cand, stack, *span)? {
+                    mask[id >> 5] |= 1 << (id & 31);
+                }
+            }
+            check(unsafe {
+                cozo_gpu_hnsw_search_filtered(
+                    staged.h, flat.as_ptr(), b as u32, k_dev as u32, config.ef as u32, config.radius.unwrap_or(-1.0),
+                    mask.as_ptr(), ids.as_mut_ptr(), dist.as_mut_ptr(), count.as_mut_ptr(), &mut stats,
+                )
+            })?;
+        } else {
+            check(unsafe {
+                cozo_gpu_hnsw_search(
+                    staged.h, flat.as_ptr(), b as u32, k_dev as u32, config.ef as u32,
+                    config.radius.unwrap_or(-1.0), // < 0: no radius
+                    ids.as_mut_ptr(), dist.as_mut_ptr(), count.as_mut_ptr(), &mut stats,
+                )
+            })?;
+        }
         let mut out = Vec::with_capacity(b);
         for qi in 0..b {
             let mut ret = vec![];
             for j in 0..count[qi] as usize {
                 let cand_key = &staged.keys[ids[qi * k_dev + j] as usize];
                 let distance = dist[qi * k_dev + j] as f64;
-                let mut cand_tuple = config
-                    .base_handle
-                    .get(self, &cand_key.0)?
-                    .ok_or_else(|| miette!("corrupted index"))?;
-                // same order as all_bindings() — hnsw.rs:958-992
-                if config.bind_field.is_some() {
-                    let field = if cand_key.1 < nk {
-                        config.base_handle.metadata.keys[cand_key.1].name.clone()
-                    } else {
-                        config.base_handle.metadata.non_keys[cand_key.1 - nk].name.clone()
-                    };
-                    cand_tuple.push(DataValue::Str(field));
-                }
-                if config.bind_field_idx.is_some() {
-                    cand_tuple.push(if cand_key.2 < 0 { DataValue::Null } else { DataValue::from(cand_key.2 as i64) });
-                }
-                if config.bind_distance.is_some() {
-                    cand_tuple.push(DataValue::from(distance));
-                }
-                if config.bind_vector.is_some() {
-                    let vec = if cand_key.2 < 0 {
-                        cand_tuple[cand_key.1].clone()
-                    } else {
-                        match &cand_tuple[cand_key.1] {
-                            DataValue::List(v) => v[cand_key.2 as usize].clone(),
-                            v => bail!("corrupted index value {:?}", v),
-                        }
-                    };
-                    cand_tuple.push(vec);
-                }
-                if let Some((code, span)) = filter_bytecode {
+                let cand_tuple = self.assemble_candidate(config, cand_key, nk, DataValue::from(distance))?;
+                if let (Some((code, span)), false) = (filter_bytecode, device_filter) {
                     if !eval_bytecode_pred(code, &cand_tuple, stack, *span)? {
                         continue;
                     }
@@ -300,6 +309,45 @@ impl<'a> SessionTx<'a> {
             out.push(ret);
         }
         Ok(out)
+    }
+}
+
+impl<'a> SessionTx<'a> {
+    /// base row ++ bindings in the order of `HnswSearch::all_bindings` (hnsw.rs:958-995, program.rs:1016-1025)
+    fn assemble_candidate(&self, config: &HnswSearch, cand_key: &CompoundKey, nk: usize, distance: DataValue) -> Result<Tuple> {
+        let mut cand_tuple = config.base_handle.get(self, &cand_key.0)?.ok_or_else(|| miette!("corrupted index"))?;
+        if config.bind_field.is_some() {
+            let field = if cand_key.1 < nk {
+                config.base_handle.metadata.keys[cand_key.1].name.clone()
+            } else {
+                config.base_handle.metadata.non_keys[cand_key.1 - nk].name.clone()
+            };
+            cand_tuple.push(DataValue::Str(field));
+        }
+        if config.bind_field_idx.is_some() {
+            cand_tuple.push(if cand_key.2 < 0 { DataValue::Null } else { DataValue::from(cand_key.2 as i64) });
+        }
+        if config.bind_distance.is_some() {
+            cand_tuple.push(distance);
+        }
+        if config.bind_vector.is_some() {
+            let vec = if cand_key.2 < 0 {
+                cand_tuple[cand_key.1].clone()
+            } else {
+                match &cand_tuple[cand_key.1] {
+                    DataValue::List(v) => v[cand_key.2 as usize].clone(),
+                    v => bail!("corrupted index value {:?}", v),
+                }
+            };
+            cand_tuple.push(vec);
+        }
+        Ok(cand_tuple)
+    }
+    /// position of the bound distance inside the candidate tuple, if it is bound at all
+    fn distance_binding_pos(&self, config: &HnswSearch) -> Option<usize> {
+        config.bind_distance.as_ref()?;
+        let arity = config.base_handle.metadata.keys.len() + config.base_handle.metadata.non_keys.len();
+        Some(arity + config.bind_field.is_some() as usize + config.bind_field_idx.is_some() as usize)
     }
 }
 

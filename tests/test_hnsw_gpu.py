@@ -92,6 +92,35 @@ def test_k_ef_radius_edges(gpu, cfg1):
     assert np.all(out[0][np.arange(64)[:, None], np.arange(10)[None, :]][~np.isfinite(out[1])] == 0xFFFFFFFF)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_filter_mask_is_applied_before_the_trim(gpu, cfg1, mode):
+    """hnsw_knn with a filter (hnsw.rs:943-947, 997-1006): the whole ef-beam is filtered, THEN the first k are kept"""
+    X, ix, g, Q = cfg1
+    n = X.shape[0]
+    rng = np.random.default_rng(99)
+    gpu.set_option("hnsw.mode", mode)
+    try:
+        full_i, full_d, full_c, _ = g.search(Q, 64, 64)                      # the unfiltered beam, nearest first
+        for frac, radius in ((0.3, None), (0.05, None), (0.5, float(np.median(full_d[:, 20])))):
+            keep = rng.random(n) < frac
+            ids, dist, cnt, st = g.search(Q, 10, 64, radius=radius, row_pass=keep)
+            for q in range(len(Q)):
+                sel = [(i, d) for i, d in zip(full_i[q, :full_c[q]], full_d[q, :full_c[q]])
+                       if keep[i] and (radius is None or d <= radius)][:10]
+                assert cnt[q] == len(sel)
+                assert ids[q, :cnt[q]].tolist() == [i for i, _ in sel]
+                assert dist[q, :cnt[q]].tolist() == [d for _, d in sel]
+                assert np.all(ids[q, cnt[q]:] == 0xFFFFFFFF) and np.all(np.isinf(dist[q, cnt[q]:]))
+        none = g.search(Q[:50], 10, 64, row_pass=np.zeros(n, bool))
+        assert np.all(none[2] == 0)
+        every = g.search(Q[:50], 10, 64, row_pass=np.ones(n, bool))
+        plain = g.search(Q[:50], 10, 64)
+        assert np.array_equal(every[0], plain[0]) and np.array_equal(every[1], plain[1])
+        assert st.dist_evals > 0                                             # the traversal itself ignores the filter
+    finally:
+        gpu.set_option("hnsw.mode", -1)
+
+
 def test_self_query_is_nearest(gpu, cfg1):
     X, ix, g, Q = cfg1
     ids, dist, cnt, _ = g.search(X[:200], 1, 64)

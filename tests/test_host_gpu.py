@@ -185,6 +185,10 @@ def test_hnsw_search_ra(h):
     for qi in range(60):
         exp = [names[j] for j in oi40[qi] if j % 7 != 0][:3]
         assert [r[2] for r in out if r[0] == qi] == exp
+    # the same filter declared independent of the distance: verdicts per row as a bit mask, trim inside the kernel
+    ra = h.HnswSearchRA(base, index, k=3, ef=40, bind_distance=True, bind_idx=1, filter=lambda r: r[2] != 0,
+                        filter_reads_distance=False)
+    assert ra.iter(parent) == out
     r0 = float(np.median(od[:, 2]))
     ra = h.HnswSearchRA(base, index, k=5, ef=40, radius=r0, bind_distance=True, bind_idx=1)
     out = ra.iter(parent)

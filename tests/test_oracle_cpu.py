@@ -341,3 +341,70 @@ def test_yen_vs_networkx():
         except nx.NetworkXNoPath:
             ref = []
         assert [p for _, p in res] == ref
+
+
+def test_reference_goldens():
+    """Pins the oracle against outputs of the REAL reference (tools/run_reference.sh: stock cozo, mem engine).
+    The files can only be produced on a machine with cargo; while they are absent the oracle stays
+    'parity unpinned'  and this test skips."""
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ph, pg = os.path.join(gdir, "reference_hnsw.json"), os.path.join(gdir, "reference_graph.json")
+    if not (os.path.exists(ph) and os.path.exists(pg)):
+        pytest.skip("tests/golden/reference_*.json not generated (needs cargo: tools/run_reference.sh)")
+    from tests.util import SEED_DATA, SEED_QUERY, uniform_vectors
+    X = uniform_vectors(10_000, 128, SEED_DATA)
+    Q = uniform_vectors(1_000, 128, SEED_QUERY)
+    ref = json.load(open(ph))
+    rows = ref["index_rows"]["rows"]      # layer, fr_k, fr__field, fr__sub_idx, to_k, to__field, to__sub_idx, dist, hash, ignore_link
+    top = -min(r[0] for r in rows if r[2] is not None)
+    adj = [dict() for _ in range(top + 1)]
+    for r in rows:
+        if r[2] is None:                  # canary
+            continue
+        L = -r[0]
+        adj[L].setdefault(r[1], [])
+        if r[4] != r[1] and not r[9]:     # hnsw_get_neighbours reading rules (hnsw.rs:609, 618-620)
+            adj[L][r[1]].append(r[4])
+    first = min((r for r in rows if r[2] is not None), key=lambda r: (r[0], r[1]))
+    node_ids, row_ptr, col_idx = [None], [], []
+    for L in range(top + 1):
+        nodes = list(range(10_000)) if L == 0 else sorted(adj[L])
+        if L:
+            node_ids.append(np.array(nodes, np.uint32))
+        rp, ci = [0], []
+        for u in nodes:
+            ci += sorted(adj[L].get(u, []))
+            rp.append(len(ci))
+        row_ptr.append(np.array(rp, np.uint64))
+        col_idx.append(np.array(ci, np.uint32))
+    ix = O.OracleHnsw.from_levels(X, O.HnswLevels(node_ids, row_ptr, col_idx, first[1]))
+    ids, dist, cnt, _ = ix.search(Q, 10, 64, n_threads=8)
+    same = 0
+    for qi, r in enumerate(ref["knn"]):
+        got = {int(k) for k in ids[qi, :cnt[qi]]}
+        want = {int(row[0]) for row in r["rows"]}
+        same += got == want
+        assert len(got & want) >= 9
+        assert np.allclose(sorted(dist[qi, :cnt[qi]]), sorted(row[1] for row in r["rows"]), rtol=1e-6)
+    assert same >= 995
+    # graph rules on air-routes
+    from tests.test_air_routes_cpu import load_routes
+    n, src, dst, w, id_of, _ = load_routes()
+    g = json.load(open(pg))
+    og = O.OracleGraph(n, src, dst)
+    want = {r[0]: r[1] for r in g["pagerank"]["rows"]}
+    for variant in ("jacobi", "gs"):
+        sc, _, _ = og.pagerank(0.85, 1e-4, 10, variant=variant)
+        err = max(abs(sc[id_of[c]] - v) / v for c, v in want.items())
+        print(f"PageRank oracle variant {variant}: max rel diff to the reference {err:.3e}")
+    sc, _, _ = og.pagerank(0.85, 1e-4, 10, variant="jacobi")
+    assert max(abs(sc[id_of[c]] - v) / v for c, v in want.items()) <= 1e-5
+    ow = O.OracleGraph(n, src, dst, w)
+    oc = ow.closeness(n_threads=8)
+    for c, v in g["closeness"]["rows"]:
+        assert (not np.isfinite(v) and not np.isfinite(oc[id_of[c]])) or abs(oc[id_of[c]] - v) <= 1e-5 * abs(v)
+    ob = ow.betweenness(n_threads=8)
+    for c, v in g["betweenness"]["rows"]:
+        assert abs(ob[id_of[c]] - v) <= 1e-4 * max(1.0, abs(v))
