@@ -74,6 +74,8 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], help="library option name=value")
     ap.add_argument("--exchange", default=os.environ.get("COZO_BENCH_EXCHANGE", "fused"), choices=["nccl", "fused"],
                     help="N>1: one NCCL all-gather per list (north star) or peer stores fused into the search kernel")
+    ap.add_argument("--also-exchange", default=None, choices=["nccl", "fused"],
+                    help="N>1: time the other exchange too on the same indexes (reported under `exchange_alt`)")
     ap.add_argument("--out", default=None, help="--impl export-graph: where to write the graph")
     ap.add_argument("--scale", type=int, default=24, help="pagerank: RMAT scale")
     a = ap.parse_args()
@@ -522,6 +524,31 @@ def main():
     units = B * a.steps * (world if a.scaling == "weak" else 1)
     value = units / (total_ms / 1e3)
 
+    # ---- the other exchange on the same shards (optional) ----------------------------------------------
+    exchange_alt = None
+    if grp is not None and a.also_exchange:
+        capi.set_option("shard.exchange", 1 if a.also_exchange == "fused" else 0)
+        uid2 = [capi.ShardGroup.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid2, src=0)
+        grp2 = capi.ShardGroup(uid2[0], rank, world)
+        grp2.attach(g)
+        for s_ in range(min(a.warmup, 2)):
+            grp2.search_dev(Qd[s_ % nsets].data_ptr(), B, k, ef, out_i.data_ptr(), out_d.data_ptr(), None, stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for i in range(a.steps):
+            grp2.search_dev(Qd[(a.warmup + i) % nsets].data_ptr(), B, k, ef, out_i.data_ptr(), out_d.data_ptr(), None, stream)
+        eb.record()
+        torch.cuda.synchronize()
+        t2 = torch.tensor([ea.elapsed_time(eb)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        exchange_alt = {"exchange": grp2.info()["exchange"], "ms_per_step": float(t2.item()) / a.steps,
+                        "value": B * a.steps * (world if a.scaling == "weak" else 1) / (float(t2.item()) / 1e3)}
+        grp2.close()
+        capi.set_option("shard.exchange", 1 if a.exchange == "fused" else 0)
+
     # ---- roofline of the dominant kernel (hnsw_search_kernel) ---------------------------
     st = qstats[a.warmup:].to(torch.int64).sum(dim=(0, 1)).cpu().numpy()
     dist_evals, expanded, nbr_reads = int(st[0]), int(st[1]), int(st[2])
@@ -660,7 +687,7 @@ def main():
             "recall_at_k_vs_oracle": recall_vs_oracle, "parity": parity,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": a.steps * (1 if world == 1 else tiles * per_tile),
-            "exchange": (info["exchange"] if info else None),
+            "exchange": (info["exchange"] if info else None), "exchange_alt": exchange_alt,
             "step_ms": step_ms,
         }
         print(json.dumps(line), flush=True)

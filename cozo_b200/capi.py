@@ -29,7 +29,7 @@ EXPORTS = [
     "cozo_gpu_betweenness", "cozo_gpu_clustering", "cozo_gpu_sssp_paths",
     "cozo_gpu_shards_unique_id", "cozo_gpu_shards_init", "cozo_gpu_shards_free", "cozo_gpu_shards_info",
     "cozo_gpu_hnsw_stage_sharded", "cozo_gpu_hnsw_search_sharded", "cozo_gpu_hnsw_search_sharded_dev",
-    "cozo_gpu_hnsw_search_filtered", "cozo_gpu_hnsw_search_filtered_dev",
+    "cozo_gpu_hnsw_search_filtered", "cozo_gpu_hnsw_search_filtered_dev", "cozo_gpu_hnsw_search_f64",
 ]
 UID_BYTES = 128
 
@@ -48,7 +48,7 @@ class HnswLevel(C.Structure):
 class HnswStageDesc(C.Structure):
     _fields_ = [("n_vectors", C.c_uint32), ("dim", C.c_uint32), ("metric", C.c_int32), ("n_levels", C.c_uint32),
                 ("levels", C.POINTER(HnswLevel)), ("vectors", C.c_void_p), ("vectors_on_device", C.c_int32),
-                ("entry_point", C.c_uint32), ("m_max0", C.c_uint32), ("m_max", C.c_uint32)]
+                ("entry_point", C.c_uint32), ("m_max0", C.c_uint32), ("m_max", C.c_uint32), ("vec_dtype", C.c_int32)]
 
 
 class SearchStats(C.Structure):
@@ -110,6 +110,7 @@ def load():
     L.cozo_gpu_sssp_paths.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
     L.cozo_gpu_hnsw_search_filtered.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, C.POINTER(SearchStats)]
     L.cozo_gpu_hnsw_search_filtered_dev.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, vp, vp]
+    L.cozo_gpu_hnsw_search_f64.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, C.POINTER(SearchStats)]
     L.cozo_gpu_shards_unique_id.argtypes = [vp]
     L.cozo_gpu_shards_init.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int]
     L.cozo_gpu_shards_free.argtypes = [vp]
@@ -185,11 +186,13 @@ class HnswIndex:
                 lv[i].node_ids = ni.ctypes.data if ni.size else None
         d = HnswStageDesc()
         if vectors_dev_ptr is None:
-            vectors = np.ascontiguousarray(vectors, np.float32)
+            f64 = np.asarray(vectors).dtype == np.float64         # an F64 index (VecElementType::F64)
+            vectors = np.ascontiguousarray(vectors, np.float64 if f64 else np.float32)
             keep.append(vectors)
             d.n_vectors, d.dim = vectors.shape
             d.vectors = vectors.ctypes.data
             d.vectors_on_device = 0
+            d.vec_dtype = 1 if f64 else 0
         else:
             d.n_vectors, d.dim = n_vectors, dim
             d.vectors = vectors_dev_ptr
@@ -311,6 +314,19 @@ class HnswIndex:
             mask = pack_row_mask(row_pass)
             _check(load().cozo_gpu_hnsw_search_filtered(self._h, _p(queries), B, k, ef, r, _p(mask), _p(ids), _p(dist),
                                                         _p(cnt), C.byref(st)))
+        return ids, dist, cnt, st
+
+    def search_f64(self, queries: np.ndarray, k: int, ef: int, radius: float | None = None, row_pass: np.ndarray | None = None):
+        """hnsw_knn on an F64 index -> ids[B,k] u32, dist[B,k] f64, count[B], SearchStats"""
+        queries = np.ascontiguousarray(queries, np.float64).reshape(-1, self.dim)
+        B = queries.shape[0]
+        ids = np.empty((B, max(k, 1)), np.uint32)
+        dist = np.empty((B, max(k, 1)), np.float64)
+        cnt = np.zeros(B, np.uint32)
+        st = SearchStats()
+        mask = None if row_pass is None else pack_row_mask(row_pass)
+        _check(load().cozo_gpu_hnsw_search_f64(self._h, _p(queries), B, k, ef, -1.0 if radius is None else float(radius),
+                                               _p(mask), _p(ids), _p(dist), _p(cnt), C.byref(st)))
         return ids, dist, cnt, st
 
     def search_dev(self, q_ptr: int, B: int, k: int, ef: int, ids_ptr: int, dist_ptr: int, count_ptr: int | None = None,

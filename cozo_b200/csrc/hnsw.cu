@@ -613,7 +613,17 @@ extern "C" int cozo_gpu_hnsw_stage(cozo_gpu_hnsw_t** out, const CozoGpuHnswStage
   } while (0)
 
   // vectors
-  if (n) {
+  if (d->vec_dtype != 0 && d->vec_dtype != 1) return fail(set_error(COZO_GPU_EINVAL, "unknown vec_dtype %d", d->vec_dtype));
+  if (d->vec_dtype == 1) {  // VecElementType::F64: f64 payloads, searched in f64 (hnsw.rs:73-76, 86-93, 102-107)
+    h->f64 = true;
+    h->ld64 = round_up(d->dim, 2);
+    if (n) {
+      STAGE_CUDA(cudaMalloc(&h->d_vec64, (size_t)n * h->ld64 * 8));
+      if (h->ld64 != g.dim) STAGE_CUDA(cudaMemset(h->d_vec64, 0, (size_t)n * h->ld64 * 8));
+      STAGE_CUDA(cudaMemcpy2D(h->d_vec64, (size_t)h->ld64 * 8, d->vectors, (size_t)g.dim * 8, (size_t)g.dim * 8, n,
+                              d->vectors_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    }
+  } else if (n) {
     STAGE_CUDA(cudaMalloc(&h->d_vec, (size_t)n * g.ld * 4));
     if (g.ld != g.dim) STAGE_CUDA(cudaMemset(h->d_vec, 0, (size_t)n * g.ld * 4));
     STAGE_CUDA(cudaMemcpy2D(h->d_vec, (size_t)g.ld * 4, d->vectors, (size_t)g.dim * 4, (size_t)g.dim * 4, n,
@@ -671,6 +681,7 @@ extern "C" void cozo_gpu_hnsw_free(cozo_gpu_hnsw_t* h) {
   if (!h) return;
   for (auto* ws : h->pool) free_ws(ws);
   if (h->d_vec && h->vec_owned) cudaFree(h->d_vec);
+  if (h->d_vec64) cudaFree(h->d_vec64);
   if (h->d_adj0) cudaFree(h->d_adj0);
   if (h->d_upper_off) cudaFree(h->d_upper_off);
   if (h->d_adj_up) cudaFree(h->d_adj_up);
@@ -686,6 +697,7 @@ extern "C" void cozo_gpu_hnsw_free(cozo_gpu_hnsw_t* h) {
 
 static int check_search_args(cozo_gpu_hnsw_t* h, uint32_t k, uint32_t ef) {
   if (!h) return set_error(COZO_GPU_EINVAL, "null index handle");
+  if (h->f64) return set_error(COZO_GPU_EINVAL, "F64 index: use cozo_gpu_hnsw_search_f64");
   // SearchInput::normalize_hnsw rejects k<=0 / ef<=0 (data/program.rs:1341-1569)
   if (k == 0) return set_error(COZO_GPU_EINVAL, "k must be positive");
   if (ef == 0) return set_error(COZO_GPU_EINVAL, "ef must be positive");

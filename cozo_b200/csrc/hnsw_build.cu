@@ -547,6 +547,8 @@ static BuildDev build_dev(cozo_gpu_hnsw* h) {
 
 // An index staged from host CSR carries no degrees / edge distances: derive them once.
 int hnsw_ensure_build_state(cozo_gpu_hnsw* h) {
+  if (h->f64)
+    return set_error(COZO_GPU_EUNSUP, "F64 indexes are search-only on the device: re-stage after a mutation");
   if (h->build_state_ready) return 0;
   HnswDev& g = h->dev;
   // staging allocated exactly n rows; move to the growable layout

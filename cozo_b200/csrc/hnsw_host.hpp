@@ -34,6 +34,10 @@ struct cozo_gpu_hnsw {
   // owned device buffers
   float* d_vec = nullptr;
   bool vec_owned = true;
+  // F64 vector index (VecElementType::F64): payloads as doubles, searched by hnsw_f64.cu only
+  double* d_vec64 = nullptr;
+  uint32_t ld64 = 0;
+  bool f64 = false;
   uint32_t* d_adj0 = nullptr;
   uint32_t* d_upper_off = nullptr;
   uint32_t* d_adj_up = nullptr;

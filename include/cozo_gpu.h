@@ -43,7 +43,7 @@ extern "C" {
 #define COZO_GPU_ENODEV (-3)   /* no sm_100 device / extension unusable        */
 #define COZO_GPU_ENOMEM (-4)   /* allocation failed                            */
 #define COZO_GPU_EKILLED (-5)  /* poison flag was set (runtime/db.rs:1933-1941) */
-#define COZO_GPU_EUNSUP (-6)   /* outside the supported envelope (e.g. F64 vectors) */
+#define COZO_GPU_EUNSUP (-6)   /* outside the supported envelope (e.g. maintenance of an F64 index) */
 
 #define COZO_GPU_NONE 0xFFFFFFFFu /* padding id in result arrays */
 #define COZO_GPU_MAX_PEERS 16     /* destinations of the fused search + exchange */
@@ -85,12 +85,14 @@ typedef struct {
   int32_t metric;         /* COZO_GPU_L2 / COSINE / IP                 */
   uint32_t n_levels;      /* >= 1; top layer = -(n_levels-1)           */
   const CozoGpuHnswLevel* levels;
-  const float* vectors;   /* row-major [n_vectors x dim] f32           */
+  const void* vectors;    /* row-major [n_vectors x dim], f32 or f64 per vec_dtype */
   int32_t vectors_on_device; /* 0: host pointer, 1: device pointer     */
   uint32_t entry_point;   /* fr part of the first index row in key order
                              (hnsw.rs:891-899); COZO_GPU_NONE = canary only = empty index */
   uint32_t m_max0;        /* 2*m, degree bound on layer 0              */
   uint32_t m_max;         /* m, degree bound above                     */
+  int32_t vec_dtype;      /* VecElementType (data/relation.rs:108): 0 = F32, 1 = F64.  An F64 index keeps f64
+                             payloads and is searched with cozo_gpu_hnsw_search_f64 only */
 } CozoGpuHnswStageDesc;
 
 typedef struct {
@@ -136,6 +138,14 @@ int cozo_gpu_hnsw_search_filtered_dev(cozo_gpu_hnsw_t* h, const float* queries_d
                                       uint32_t ef, double radius, const uint32_t* row_mask_dev, uint32_t* out_ids_dev,
                                       float* out_dist_dev, uint32_t* out_count_dev, uint32_t* per_query_stats_dev,
                                       void* stream);
+
+/* hnsw_knn on an F64 index (manifest.dtype == F64): the query is f64 (an F32 query is widened by the caller,
+ * hnsw.rs:879-884), distances are computed and returned in f64 (hnsw.rs:73-76, 86-93, 102-107).  row_mask as in
+ * cozo_gpu_hnsw_search_filtered, nullable.  F64 indexes are search-only on the device: insert / update / remove
+ * answer COZO_GPU_EUNSUP and the host re-stages after a mutation. */
+int cozo_gpu_hnsw_search_f64(cozo_gpu_hnsw_t* h, const double* queries, uint32_t B, uint32_t k, uint32_t ef,
+                             double radius, const uint32_t* row_mask, uint32_t* out_ids, double* out_dist,
+                             uint32_t* out_count, CozoGpuSearchStats* stats);
 
 /* Sharded corpus, fused search + exchange: the search kernel stores the top-k of
  * every query straight into the [n_slots][B][k] gather buffers of all `n_dest` destinations at

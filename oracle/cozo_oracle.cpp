@@ -103,6 +103,37 @@ static double vec_dist(int metric, const float* a, const float* b, size_t n) {
   }
 }
 
+// F64 vector indexes (hnsw.rs:73-76, 86-93, 102-107): the same expressions with f64 operands throughout;
+// ndarray's unrolled_dot is generic over the element type, so the accumulator structure is the same.
+static double unrolled_dot64(const double* x, const double* y, size_t n) {
+  double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8)
+    for (int j = 0; j < 8; ++j) p[j] = p[j] + x[i + j] * y[i + j];
+  double sum = 0;
+  sum = sum + (p[0] + p[4]);
+  sum = sum + (p[1] + p[5]);
+  sum = sum + (p[2] + p[6]);
+  sum = sum + (p[3] + p[7]);
+  for (; i < n; ++i) sum = sum + x[i] * y[i];
+  return sum;
+}
+static double vec_dist64(int metric, const double* a, const double* b, size_t n) {
+  switch (metric) {
+    case L2: {  // hnsw.rs:73-76: diff = a - b (materialised), diff.dot(&diff)
+      std::vector<double> diff(n);
+      for (size_t i = 0; i < n; ++i) diff[i] = a[i] - b[i];
+      return unrolled_dot64(diff.data(), diff.data(), n);
+    }
+    case COSINE: {  // hnsw.rs:86-91
+      double an = unrolled_dot64(a, a, n), bn = unrolled_dot64(b, b, n), dot = unrolled_dot64(a, b, n);
+      return 1.0 - dot / std::sqrt(an * bn);
+    }
+    default:  // hnsw.rs:102-105
+      return 1.0 - unrolled_dot64(a, b, n);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // priority-queue 1.4.0 stand-in (Cargo.lock:2836).  push = insert-or-replace,
 // pop/peek = max priority.  Order among EQUAL priorities is unspecified in the
@@ -211,7 +242,8 @@ struct SearchStats {
 };
 
 // a4. hnsw_search_level — hnsw.rs:539-587
-static void search_level(const HnswView& ix, const float* q, size_t ef, uint32_t level,
+template <class Dist>  // Dist: double(uint32_t id) = VectorCache::v_dist(q, id)
+static void search_level(const HnswView& ix, Dist&& dist_to, size_t ef, uint32_t level,
                          MaxPQ& found_nn, SearchStats& st) {
   std::unordered_set<uint32_t> visited;
   MinPQ candidates;
@@ -230,7 +262,7 @@ static void search_level(const HnswView& ix, const float* q, size_t ef, uint32_t
     for (uint64_t i = b; i < e; ++i) {  // key order, hnsw.rs:566
       uint32_t nb = lv.col_idx[i];
       if (visited.count(nb)) continue;
-      double d = vec_dist(ix.metric, q, ix.vec(nb), ix.dim);
+      double d = dist_to(nb);
       st.dist_evals++;
       double far = found_nn.peek().second;  // read BEFORE insertion, hnsw.rs:574
       if (found_nn.size() < ef || d < far) {
@@ -246,16 +278,17 @@ static void search_level(const HnswView& ix, const float* q, size_t ef, uint32_t
 // a5. hnsw_knn — hnsw.rs:869-1012, minus the base-row fetch / bind_* columns /
 // filter bytecode which are host-engine work.  `k_eff` is k, or ef when a
 // filter is present (hnsw.rs:943-947).  Output nearest-first (hnsw.rs:1005).
-static uint32_t hnsw_knn(const HnswView& ix, const float* q, uint32_t k, uint32_t ef, double radius,
-                         bool has_radius, uint32_t* out_ids, double* out_dist, SearchStats& st) {
+template <class Dist>
+static uint32_t hnsw_knn_with(const HnswView& ix, Dist&& dist_to, uint32_t k, uint32_t ef, double radius,
+                              bool has_radius, uint32_t* out_ids, double* out_dist, SearchStats& st) {
   if (ix.empty_index || ix.entry == UINT32_MAX) return 0;  // hnsw.rs:903-909,1009
   MaxPQ found_nn;
-  double ep_d = vec_dist(ix.metric, q, ix.vec(ix.entry), ix.dim);
+  double ep_d = dist_to(ix.entry);
   st.dist_evals++;
   found_nn.push(ix.entry, ep_d);  // hnsw.rs:916-918
   for (uint32_t lvl = (uint32_t)ix.levels.size() - 1; lvl >= 1; --lvl)  // hnsw.rs:919-929
-    search_level(ix, q, 1, lvl, found_nn, st);
-  search_level(ix, q, ef, 0, found_nn, st);  // hnsw.rs:930-938
+    search_level(ix, dist_to, 1, lvl, found_nn, st);
+  search_level(ix, dist_to, ef, 0, found_nn, st);  // hnsw.rs:930-938
   while (found_nn.size() > k) found_nn.pop();  // hnsw.rs:943-947
   std::vector<std::pair<uint32_t, double>> ret;
   while (!found_nn.empty()) {  // hnsw.rs:951-1004
@@ -270,6 +303,12 @@ static uint32_t hnsw_knn(const HnswView& ix, const float* q, uint32_t k, uint32_
     out_dist[i] = ret[i].second;
   }
   return (uint32_t)ret.size();
+}
+
+static uint32_t hnsw_knn(const HnswView& ix, const float* q, uint32_t k, uint32_t ef, double radius,
+                         bool has_radius, uint32_t* out_ids, double* out_dist, SearchStats& st) {
+  return hnsw_knn_with(ix, [&](uint32_t id) { return vec_dist(ix.metric, q, ix.vec(id), ix.dim); }, k, ef, radius,
+                       has_radius, out_ids, out_dist, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -1103,6 +1142,35 @@ const float* orc_hnsw_vectors(void* hp) {
   auto* h = (HnswHandle*)hp;
   h->ensure_view();
   return h->view.vectors;
+}
+
+// -- F64 index: the same graph, f64 payloads and queries (manifest.dtype == F64, hnsw.rs:879-884) -------------
+int orc_hnsw_search_batch_f64(void* hp, const double* vectors64, const double* queries, uint32_t B, uint32_t k,
+                              uint32_t ef, double radius, uint32_t* out_ids, double* out_dist, uint32_t* out_count,
+                              uint64_t* stats, uint32_t n_threads) {
+  auto* h = (HnswHandle*)hp;
+  h->ensure_view();
+  const HnswView& ix = h->view;
+  parallel_for(B, n_threads, [&](uint32_t qi, unsigned) {
+    SearchStats st;
+    uint32_t* ids = out_ids + (size_t)qi * k;
+    double* ds = out_dist + (size_t)qi * k;
+    for (uint32_t j = 0; j < k; ++j) {
+      ids[j] = UINT32_MAX;
+      ds[j] = INFINITY;
+    }
+    const double* q = queries + (size_t)qi * ix.dim;
+    uint32_t c = hnsw_knn_with(
+        ix, [&](uint32_t id) { return vec_dist64(ix.metric, q, vectors64 + (size_t)id * ix.dim, ix.dim); }, k, ef, radius,
+        radius >= 0, ids, ds, st);
+    if (out_count) out_count[qi] = c;
+    if (stats) {
+      stats[(size_t)qi * 3 + 0] = st.dist_evals;
+      stats[(size_t)qi * 3 + 1] = st.nodes_expanded;
+      stats[(size_t)qi * 3 + 2] = st.nbr_reads;
+    }
+  });
+  return 0;
 }
 
 // -- search -------------------------------------------------------------------

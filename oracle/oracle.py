@@ -58,6 +58,8 @@ def lib():
         L.orc_hnsw_export_level.argtypes = [vp, u32, vp, vp, vp]
         L.orc_hnsw_search_batch.restype = C.c_int
         L.orc_hnsw_search_batch.argtypes = [vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, u32]
+        L.orc_hnsw_search_batch_f64.restype = C.c_int
+        L.orc_hnsw_search_batch_f64.argtypes = [vp, vp, vp, u32, u32, u32, f64, vp, vp, vp, vp, u32]
         L.orc_bruteforce_knn.restype = C.c_int
         L.orc_bruteforce_knn.argtypes = [vp, u32, u32, C.c_int, vp, u32, u32, vp, vp, u32]
         L.orc_graph_new.restype = vp
@@ -203,6 +205,22 @@ class OracleHnsw:
         stats = np.zeros((B, 3), np.uint64)
         rc = lib().orc_hnsw_search_batch(self._h, _p(queries), B, k, ef, -1.0 if radius is None else float(radius),
                                          _p(ids), _p(dist), _p(cnt), _p(stats), n_threads)
+        assert rc == 0
+        return ids, dist, cnt, stats
+
+    def search_f64(self, vectors64: np.ndarray, queries: np.ndarray, k: int, ef: int, radius: float | None = None,
+                   n_threads: int = 1):
+        """the same graph searched as an F64 index (manifest.dtype == F64): f64 payloads, f64 queries, f64 arithmetic"""
+        vectors64 = np.ascontiguousarray(vectors64, np.float64).reshape(-1, self.dim)
+        queries = np.ascontiguousarray(queries, np.float64).reshape(-1, self.dim)
+        B = queries.shape[0]
+        ids = np.empty((B, k), np.uint32)
+        dist = np.empty((B, k), np.float64)
+        cnt = np.zeros(B, np.uint32)
+        stats = np.zeros((B, 3), np.uint64)
+        rc = lib().orc_hnsw_search_batch_f64(self._h, _p(vectors64), _p(queries), B, k, ef,
+                                             -1.0 if radius is None else float(radius), _p(ids), _p(dist), _p(cnt),
+                                             _p(stats), n_threads)
         assert rc == 0
         return ids, dist, cnt, stats
 

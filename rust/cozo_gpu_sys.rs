@@ -37,11 +37,12 @@ pub struct CozoGpuHnswStageDesc {
     pub metric: i32,
     pub n_levels: u32,
     pub levels: *const CozoGpuHnswLevel,
-    pub vectors: *const f32,
+    pub vectors: *const c_void,
     pub vectors_on_device: i32,
     pub entry_point: u32,
     pub m_max0: u32,
     pub m_max: u32,
+    pub vec_dtype: i32,
 }
 
 #[repr(C)]
@@ -84,6 +85,7 @@ extern "C" {
     pub fn cozo_gpu_hnsw_search_dev(h: *mut CozoGpuHnsw, queries_dev: *const f32, B: u32, k: u32, ef: u32, radius: f64, out_ids_dev: *mut u32, out_dist_dev: *mut f32, out_count_dev: *mut u32, per_query_stats_dev: *mut u32, stream: *mut c_void) -> c_int;
     pub fn cozo_gpu_hnsw_search_filtered(h: *mut CozoGpuHnsw, queries: *const f32, B: u32, k: u32, ef: u32, radius: f64, row_mask: *const u32, out_ids: *mut u32, out_dist: *mut f32, out_count: *mut u32, stats: *mut CozoGpuSearchStats) -> c_int;
     pub fn cozo_gpu_hnsw_search_filtered_dev(h: *mut CozoGpuHnsw, queries_dev: *const f32, B: u32, k: u32, ef: u32, radius: f64, row_mask_dev: *const u32, out_ids_dev: *mut u32, out_dist_dev: *mut f32, out_count_dev: *mut u32, per_query_stats_dev: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn cozo_gpu_hnsw_search_f64(h: *mut CozoGpuHnsw, queries: *const f64, B: u32, k: u32, ef: u32, radius: f64, row_mask: *const u32, out_ids: *mut u32, out_dist: *mut f64, out_count: *mut u32, stats: *mut CozoGpuSearchStats) -> c_int;
     pub fn cozo_gpu_hnsw_search_scatter_dev(h: *mut CozoGpuHnsw, queries_dev: *const f32, B: u32, k: u32, ef: u32, radius: f64, n_dest: u32, dest_ids_ptrs: *const u64, dest_dist_ptrs: *const u64, slot: u32, per_query_stats_dev: *mut u32, stream: *mut c_void) -> c_int;
     pub fn cozo_gpu_hnsw_build(out: *mut *mut CozoGpuHnsw, desc: *const CozoGpuHnswBuildDesc) -> c_int;
     pub fn cozo_gpu_hnsw_insert(h: *mut CozoGpuHnsw, vectors: *const f32, count: u32, vectors_on_device: i32, ef_construction: u32, keep_pruned_connections: i32, first_id: *mut u32) -> c_int;

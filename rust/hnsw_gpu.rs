@@ -48,6 +48,8 @@ pub(crate) struct StagedIndex {
     keys: Vec<CompoundKey>,
     /// (base relation id, index relation id) the copy was staged from.
     stamp: (u64, u64),
+    /// manifest.dtype == F64: distances in f64 through cozo_gpu_hnsw_search_f64
+    f64_index: bool,
 }
 
 /// The reference keeps no index version counter, so the device copy is dropped AT the mutation sites
@@ -104,9 +106,7 @@ impl StagedIndex {
         mf: &HnswIndexManifest,
         stamp: (u64, u64),
     ) -> Result<Self> {
-        if mf.dtype != VecElementType::F32 {
-            bail!("gpu-b200: F64 vector indexes are outside the device envelope");
-        }
+        let f64_index = mf.dtype == VecElementType::F64; // f64 payloads, searched by cozo_gpu_hnsw_search_f64
         let k = base.metadata.keys.len();
         // index rows: (layer, fr_k.., fr__field, fr__sub_idx, to_k.., to__field, to__sub_idx,
         //              dist, hash, ignore_link)   — runtime/relation.rs:1064-1126
@@ -163,7 +163,8 @@ impl StagedIndex {
             row.push(*ids.get(&to).ok_or_else(|| miette!("corrupted index"))?);
         }
         // vectors: VectorCache::ensure_key (hnsw.rs:122-151)
-        let mut vectors = vec![0f32; n * mf.vec_dim];
+        let mut vectors = vec![0f32; if f64_index { 0 } else { n * mf.vec_dim }];
+        let mut vectors64 = vec![0f64; if f64_index { n * mf.vec_dim } else { 0 }];
         for (i, key) in keys.iter().enumerate() {
             let row = base.get(tx, &key.0)?.ok_or_else(|| miette!("Cannot find compound key for HNSW"))?;
             let field = if key.2 >= 0 {
@@ -175,8 +176,11 @@ impl StagedIndex {
                 &row[key.1]
             };
             match field {
-                DataValue::Vec(Vector::F32(v)) if v.len() == mf.vec_dim => {
+                DataValue::Vec(Vector::F32(v)) if v.len() == mf.vec_dim && !f64_index => {
                     vectors[i * mf.vec_dim..(i + 1) * mf.vec_dim].copy_from_slice(v.as_slice().unwrap())
+                }
+                DataValue::Vec(Vector::F64(v)) if v.len() == mf.vec_dim && f64_index => {
+                    vectors64[i * mf.vec_dim..(i + 1) * mf.vec_dim].copy_from_slice(v.as_slice().unwrap())
                 }
                 d => bail!("Cannot interpret {} as vector", d),
             }
@@ -215,15 +219,16 @@ impl StagedIndex {
             metric: metric_code(mf.distance),
             n_levels: n_levels as u32,
             levels: levels.as_ptr(),
-            vectors: vectors.as_ptr(),
+            vectors: if f64_index { vectors64.as_ptr() as *const _ } else { vectors.as_ptr() as *const _ },
             vectors_on_device: 0,
             entry_point: entry,
             m_max0: mf.m_max0 as u32,
             m_max: mf.m_max as u32,
+            vec_dtype: f64_index as i32,
         };
         let mut h = ptr::null_mut();
         check(unsafe { cozo_gpu_hnsw_stage(&mut h, &desc) })?;
-        Ok(StagedIndex { h, keys, stamp })
+        Ok(StagedIndex { h, keys, stamp, f64_index })
     }
 }
 
@@ -238,17 +243,21 @@ impl<'a> SessionTx<'a> {
         stack: &mut Vec<DataValue>,
     ) -> Result<Vec<Vec<Tuple>>> {
         let dim = config.manifest.vec_dim;
-        let mut flat = Vec::with_capacity(qs.len() * dim);
+        let staged = StagedIndex::get_or_stage(self, &config.base_handle, &config.idx_handle, &config.manifest)?;
+        // the query is cast to the index dtype (hnsw.rs:879-884)
+        let mut flat = Vec::with_capacity(if staged.f64_index { 0 } else { qs.len() * dim });
+        let mut flat64 = Vec::with_capacity(if staged.f64_index { qs.len() * dim } else { 0 });
         for q in qs {
             if q.len() != dim {
                 bail!("query vector dimension mismatch"); // hnsw.rs:876-878
             }
-            match q {
-                Vector::F32(v) => flat.extend(v.iter().copied()),
-                Vector::F64(v) => flat.extend(v.iter().map(|x| *x as f32)), // hnsw.rs:883
+            match (q, staged.f64_index) {
+                (Vector::F32(v), false) => flat.extend(v.iter().copied()),
+                (Vector::F64(v), false) => flat.extend(v.iter().map(|x| *x as f32)), // hnsw.rs:883
+                (Vector::F32(v), true) => flat64.extend(v.iter().map(|x| *x as f64)), // hnsw.rs:882
+                (Vector::F64(v), true) => flat64.extend(v.iter().copied()),
             }
         }
-        let staged = StagedIndex::get_or_stage(self, &config.base_handle, &config.idx_handle, &config.manifest)?;
         // With a filter the reference keeps all ef results and filters before truncating to k
         // (hnsw.rs:942-946, 1001-1008).  If the bytecode never reads the bound distance, its verdict is a
         // property of the indexed row: evaluate it once per row, ship the verdicts as a bit mask and let the
@@ -265,17 +274,29 @@ impl<'a> SessionTx<'a> {
         let b = qs.len();
         let mut ids = vec![COZO_GPU_NONE; b * k_dev];
         let mut dist = vec![0f32; b * k_dev];
+        let mut dist64 = vec![0f64; if staged.f64_index { b * k_dev } else { 0 }];
         let mut count = vec![0u32; b];
         let mut stats = CozoGpuSearchStats::default();
+        let mut mask = vec![];
         if device_filter {
             let (code, span) = filter_bytecode.as_ref().unwrap();
-            let mut mask = vec![0u32; (staged.keys.len() + 31) / 32 + 1];
+            mask = vec![0u32; (staged.keys.len() + 31) / 32 + 1];
             for (id, key) in staged.keys.iter().enumerate() {
                 let cand = self.assemble_candidate(config, key, nk, DataValue::Null)?; // distance slot unused by the filter
                 if eval_bytecode_pred(code, &cand, stack, *span)? {
                     mask[id >> 5] |= 1 << (id & 31);
                 }
             }
+        }
+        if staged.f64_index {
+            check(unsafe {
+                cozo_gpu_hnsw_search_f64(
+                    staged.h, flat64.as_ptr(), b as u32, k_dev as u32, config.ef as u32, config.radius.unwrap_or(-1.0),
+                    if device_filter { mask.as_ptr() } else { ptr::null() },
+                    ids.as_mut_ptr(), dist64.as_mut_ptr(), count.as_mut_ptr(), &mut stats,
+                )
+            })?;
+        } else if device_filter {
             check(unsafe {
                 cozo_gpu_hnsw_search_filtered(
                     staged.h, flat.as_ptr(), b as u32, k_dev as u32, config.ef as u32, config.radius.unwrap_or(-1.0),
@@ -296,7 +317,7 @@ impl<'a> SessionTx<'a> {
             let mut ret = vec![];
             for j in 0..count[qi] as usize {
                 let cand_key = &staged.keys[ids[qi * k_dev + j] as usize];
-                let distance = dist[qi * k_dev + j] as f64;
+                let distance = if staged.f64_index { dist64[qi * k_dev + j] } else { dist[qi * k_dev + j] as f64 };
                 let cand_tuple = self.assemble_candidate(config, cand_key, nk, DataValue::from(distance))?;
                 if let (Some((code, span)), false) = (filter_bytecode, device_filter) {
                     if !eval_bytecode_pred(code, &cand_tuple, stack, *span)? {

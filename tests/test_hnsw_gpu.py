@@ -121,6 +121,49 @@ def test_filter_mask_is_applied_before_the_trim(gpu, cfg1, mode):
         gpu.set_option("hnsw.mode", -1)
 
 
+@pytest.mark.parametrize("metric,dim", [(O.L2, 40), (O.COSINE, 37), (O.IP, 64)])
+def test_f64_index_parity(gpu, metric, dim):
+    """F64 vector indexes (manifest.dtype == F64): f64 payloads and queries, distances computed and returned in f64
+    (hnsw.rs:73-76, 86-93, 102-107, 879-884).  Parity vs the oracle's f64 path on the same graph."""
+    n, m = 3000, 8
+    rng = np.random.default_rng(4040 + metric)
+    X64 = rng.random((n, dim)) + (1.0 if metric != O.L2 else 0.0)
+    X64 += rng.random((n, dim)) * 1e-9                      # structure below f32 resolution
+    ix = O.OracleHnsw.new(n, dim, m=m, ef_construction=60, metric=metric)
+    ix.insert_all(X64.astype(np.float32))                   # any valid graph will do: parity is about the search
+    lv = ix.levels()
+    g = gpu.HnswIndex.stage(X64, lv.node_ids, lv.row_ptr, lv.col_idx, lv.entry, metric=metric, m_max0=2 * m, m_max=m)
+    Q64 = rng.random((200, dim)) + (1.0 if metric != O.L2 else 0.0)
+    ids, dist, cnt, st = g.search_f64(Q64, 10, 50)
+    oi, od, oc, ost = ix.search_f64(X64, Q64, 10, 50, n_threads=8)
+    assert dist.dtype == np.float64 and np.array_equal(cnt, oc)
+    assert np.mean([set(a) == set(b) for a, b in zip(ids, oi)]) >= 0.99 and recall(ids, oi) >= 0.999
+    assert np.allclose(dist, od, rtol=1e-12, atol=1e-15)
+    assert abs(int(st.dist_evals) - int(ost[:, 0].sum())) <= 0.001 * int(ost[:, 0].sum())
+    assert np.all(np.diff(dist, axis=1) >= 0)
+    # radius and filter verdicts, before the trim to k
+    r = float(np.median(od[:, 4]))
+    keep = rng.random(n) < 0.4
+    fi, fdist, fc, _ = g.search_f64(Q64, 5, 50, radius=r, row_pass=keep)
+    full_i, full_d, full_c, _ = ix.search_f64(X64, Q64, 50, 50, n_threads=8)
+    for q in range(len(Q64)):
+        sel = [(i, d) for i, d in zip(full_i[q, :full_c[q]], full_d[q, :full_c[q]]) if keep[i] and d <= r][:5]
+        assert fc[q] == len(sel)
+        if recall(ids[q:q + 1], oi[q:q + 1]) == 1.0:
+            assert fi[q, :fc[q]].tolist() == [i for i, _ in sel]
+    # the f32 entry points refuse an F64 handle loudly; maintenance is outside the envelope
+    with pytest.raises(gpu.CozoGpuError) as e:
+        g.search(Q64.astype(np.float32), 10, 50)
+    assert e.value.code == gpu.E_INVAL
+    with pytest.raises(gpu.CozoGpuError) as e:
+        g.insert(X64[:4].astype(np.float32), ef_construction=50)
+    assert e.value.code == gpu.E_UNSUP
+    # an f32 index refuses the f64 call
+    g32 = _stage(gpu, X64.astype(np.float32), lv, metric, m)
+    with pytest.raises(gpu.CozoGpuError):
+        g32.search_f64(Q64, 10, 50)
+
+
 def test_self_query_is_nearest(gpu, cfg1):
     X, ix, g, Q = cfg1
     ids, dist, cnt, _ = g.search(X[:200], 1, 64)
