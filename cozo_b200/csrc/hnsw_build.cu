@@ -52,6 +52,13 @@ struct BuildDev {
   const uint8_t* node_level;
   uint32_t m_max0, m_max;
   int keep_pruned;
+  // extend_candidates (hnsw.rs:499-511): per-task scratch of `ext_cap` (a power of two) entries each
+  int extend;
+  const uint32_t* upper_off;
+  unsigned long long* ext_keys;
+  float* ext_d;
+  uint32_t* ext_id;
+  uint32_t ext_cap;
 };
 
 struct BatchParams {
@@ -197,6 +204,114 @@ __device__ __forceinline__ uint32_t heuristic_select(const HnswDev& g, const flo
   return ns;
 }
 
+// ---- extend_candidates (hnsw.rs:499-511) ----------------------------------------------------------------------
+// candidates = found ∪ neighbours(found) at the layer, every distance to the base vector (re)computed, popped nearest
+// first.  A fidelity mode for small indexes: it multiplies the distance evaluations of selection by the degree
+// (the reference pays the same), so the builder restricts it to small batches.  The base vector's own key is skipped:
+// the reference's shrink path would admit it (and overwrite its self-loop row, hnsw.rs:413-432), which the oracle
+// treats as a defect too.
+__device__ __forceinline__ uint32_t f32_order_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_order_key(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+// bitonic sort of n (a power of two) u64 keys by one warp
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* a, uint32_t n, int lane) {
+  for (uint32_t k = 2; k <= n; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = a[i], y = a[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) {
+            a[i] = y;
+            a[ixj] = x;
+          }
+        }
+      }
+      __syncwarp();
+    }
+}
+// Builds the extended, distance-sorted candidate list of `task` in its scratch slice; returns its length.
+// base_d / base_id: the found list (ascending); q: the base vector; self: its id.
+template <int NV, int METRIC>
+__device__ __forceinline__ uint32_t extend_candidate_list(const HnswDev& g, const BuildDev& b, const float4 (&q)[NV],
+                                                          float qnorm, uint32_t self, uint32_t level, const float* base_d,
+                                                          const uint32_t* base_id, uint32_t cnt, size_t task, int lane) {
+  unsigned long long* keys = b.ext_keys + task * b.ext_cap;
+  float* cd = b.ext_d + task * b.ext_cap;
+  uint32_t* cid = b.ext_id + task * b.ext_cap;
+  const uint32_t cap = b.ext_cap;
+  const int nvec4 = g.ld >> 2;
+  // A. raw ids: the found items (they carry their distance) and every neighbour of a found item
+  for (uint32_t i = lane; i < cnt && i < cap; i += 32) keys[i] = ((unsigned long long)(base_id[i] & IDMASK) << 32) | i;
+  uint32_t nraw = cnt < cap ? cnt : cap;
+  const uint32_t stride = level == 0 ? g.s0 : g.su;
+  for (uint32_t f = 0; f < cnt; ++f) {
+    const uint32_t fid = base_id[f] & IDMASK;
+    const uint32_t* row = level == 0 ? b.adj0 + (size_t)fid * g.s0 : b.adj_up + (size_t)(b.upper_off[fid] + level - 1) * g.su;
+    for (uint32_t nb = 0; nb < stride; nb += 32) {
+      const uint32_t id = row[nb + lane];
+      if (!__ballot_sync(0xffffffffu, id != NONE)) break;
+      const bool ok = id != NONE && id != self;
+      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+      const uint32_t pos = nraw + __popc(bal & ((1u << lane) - 1));
+      if (ok && pos < cap) keys[pos] = ((unsigned long long)id << 32) | 0xFFFFFFFFull;
+      nraw += __popc(bal);
+    }
+  }
+  if (nraw > cap) nraw = cap;
+  uint32_t n2 = 32;
+  while (n2 < nraw) n2 <<= 1;
+  for (uint32_t i = nraw + lane; i < n2; i += 32) keys[i] = ~0ull;
+  __syncwarp();
+  warp_bitonic_sort(keys, n2, lane);  // by (id, origin): a found item precedes the neighbour copies of the same id
+  // B. unique ids; distances: known for found items, computed for the rest
+  uint32_t nu = 0;
+  for (uint32_t base = 0; base < nraw; base += 32) {
+    const uint32_t i = base + lane;
+    const unsigned long long k = i < nraw ? keys[i] : ~0ull;
+    const uint32_t id = (uint32_t)(k >> 32);
+    const uint32_t prev = (i > 0 && i < nraw) ? (uint32_t)(keys[i - 1] >> 32) : NONE;
+    const bool keep = i < nraw && id != prev;
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    const uint32_t pos = nu + __popc(bal & ((1u << lane) - 1));
+    if (keep) {
+      cid[pos] = id;
+      const uint32_t origin = (uint32_t)k;
+      cd[pos] = origin != 0xFFFFFFFFu ? base_d[origin] : __int_as_float(0x7FC00000);
+    }
+    nu += __popc(bal);
+  }
+  __syncwarp();
+  for (uint32_t i = 0; i < nu; ++i) {
+    float d = cd[i];
+    if (d != d) {  // not yet known (warp-uniform: every lane reads the same slot)
+      d = dist_ldg1<NV, METRIC>(q, reinterpret_cast<const float4*>(g.vec + (size_t)cid[i] * g.ld), lane, nvec4, qnorm);
+      __syncwarp();
+      if (lane == 0) cd[i] = d;
+    }
+  }
+  __syncwarp();
+  // C. nearest first (ties by id)
+  n2 = 32;
+  while (n2 < nu) n2 <<= 1;
+  for (uint32_t i = lane; i < n2; i += 32)
+    keys[i] = i < nu ? (((unsigned long long)f32_order_key(cd[i]) << 32) | cid[i]) : ~0ull;
+  __syncwarp();
+  warp_bitonic_sort(keys, n2, lane);
+  for (uint32_t i = lane; i < nu; i += 32) {
+    const unsigned long long k = keys[i];
+    cd[i] = f32_from_order_key((uint32_t)(k >> 32));
+    cid[i] = (uint32_t)k;
+  }
+  __syncwarp();
+  return nu;
+}
+
 __device__ __forceinline__ void adj_row(const HnswDev& g, const BuildDev& b, uint32_t node, uint32_t level,
                                         uint32_t*& ids, float*& ds, uint32_t*& deg, uint32_t& stride, uint32_t& mm) {
   if (level == 0) {
@@ -232,8 +347,18 @@ __global__ void __launch_bounds__(128) build_select_kernel(HnswDev g, BuildDev b
   uint32_t stride, mm;
   adj_row(g, b, node, level, ids, ds, deg, stride, mm);
   const size_t list = (size_t)t * p.ef_c;
-  uint32_t ns = heuristic_select<NV, METRIC>(g, p.cand_d + list, p.cand_id + list, p.cand_cnt[t], mm,
-                                             b.keep_pruned != 0, sel_id, sel_d, lane);
+  const float* cd = p.cand_d + list;
+  uint32_t* cid = p.cand_id + list;
+  uint32_t ccnt = p.cand_cnt[t];
+  if (b.extend) {  // hnsw.rs:499-511
+    float4 q[NV];
+    float qn;
+    load_query<NV>(g.vec + (size_t)node * g.ld, g.ld, lane, q, qn);
+    ccnt = extend_candidate_list<NV, METRIC>(g, b, q, qn, node, level, cd, cid, ccnt, t, lane);
+    cd = b.ext_d + (size_t)t * b.ext_cap;
+    cid = b.ext_id + (size_t)t * b.ext_cap;
+  }
+  uint32_t ns = heuristic_select<NV, METRIC>(g, cd, cid, ccnt, mm, b.keep_pruned != 0, sel_id, sel_d, lane);
   __syncwarp();
   uint32_t rbase = 0;
   if (lane == 0) {
@@ -328,7 +453,17 @@ __global__ void __launch_bounds__(128) build_link_kernel(HnswDev g, BuildDev b, 
       s_d[rank] = dj;
     }
     __syncwarp();
-    uint32_t ns = heuristic_select<NV, METRIC>(g, s_d, s_id, nc, mm, b.keep_pruned != 0, sel_id, sel_d, lane);
+    uint32_t ns;
+    if (b.extend) {  // hnsw_shrink_neighbour selects through the same routine, extension included (hnsw.rs:394-409)
+      float4 q[NV];
+      float qn;
+      load_query<NV>(g.vec + (size_t)node * g.ld, g.ld, lane, q, qn);
+      const uint32_t ne = extend_candidate_list<NV, METRIC>(g, b, q, qn, node, level, s_d, s_id, nc, h, lane);
+      ns = heuristic_select<NV, METRIC>(g, b.ext_d + (size_t)h * b.ext_cap, b.ext_id + (size_t)h * b.ext_cap, ne, mm,
+                                        b.keep_pruned != 0, sel_id, sel_d, lane);
+    } else {
+      ns = heuristic_select<NV, METRIC>(g, s_d, s_id, nc, mm, b.keep_pruned != 0, sel_id, sel_d, lane);
+    }
     __syncwarp();
     for (uint32_t j = lane; j < stride; j += 32) {
       bool in = j < ns;
@@ -542,6 +677,8 @@ static BuildDev build_dev(cozo_gpu_hnsw* h) {
   b.m_max0 = h->m_max0;
   b.m_max = h->m_max;
   b.keep_pruned = h->keep_pruned;
+  b.extend = 0;
+  b.upper_off = h->d_upper_off;
   return b;
 }
 
@@ -612,7 +749,11 @@ int hnsw_insert_range(cozo_gpu_hnsw* h, uint32_t begin, uint32_t end, uint32_t m
   if (rc) return rc;
   BuildDev b = build_dev(h);
   const uint32_t ef_c = h->ef_construction;
+  const bool extend = h->extend_candidates != 0;
   if (!max_batch) max_batch = 8192;
+  // extend_candidates reads the rows of OTHER nodes while selecting, so its result depends on the order in which
+  // the reference links the new node's neighbours: one node per batch, in-edges linked one at a time in selection order
+  if (extend) max_batch = 1;
   uint32_t wpc = (uint32_t)get_option("hnsw.warps_per_cta", 4);
   wpc = std::min(4u, std::max(1u, wpc));
   uint32_t ns = (uint32_t)get_option("hnsw.stages", 4);
@@ -641,11 +782,14 @@ int hnsw_insert_range(cozo_gpu_hnsw* h, uint32_t begin, uint32_t end, uint32_t m
     uint32_t *req_src = nullptr, *perm = nullptr, *perm2 = nullptr, *heads = nullptr, *counters = nullptr;
     float* req_d = nullptr;
     void* cub_tmp = nullptr;
+    unsigned long long* ext_keys = nullptr;
+    float* ext_d = nullptr;
+    uint32_t* ext_id = nullptr;
     cozo_gpu_hnsw* h = nullptr;
     HnswWorkspace* ws = nullptr;
     ~Scratch() {
       void* ptrs[] = {coff, list_node, list_level, cand_d, cand_id, cand_cnt, req_key, req_key2,
-                      req_src, perm, perm2, heads, counters, req_d, cub_tmp};
+                      req_src, perm, perm2, heads, counters, req_d, cub_tmp, ext_keys, ext_d, ext_id};
       for (void* p : ptrs)
         if (p) cudaFree(p);
       if (ws) hnsw_release_ws(h, ws);
@@ -682,6 +826,20 @@ int hnsw_insert_range(cozo_gpu_hnsw* h, uint32_t begin, uint32_t end, uint32_t m
   H_CUDA(cudaMalloc(&sc.perm2, req_cap * 4));
   H_CUDA(cudaMalloc(&sc.heads, req_cap * 4));
   H_CUDA(cudaMalloc(&sc.counters, 64));
+  if (extend) {
+    uint32_t cap = 32;
+    const uint32_t need = std::max(ef_c, mcap + 32) * (1 + std::max(g.s0, g.su));
+    while (cap < need) cap <<= 1;
+    b.extend = 1;
+    b.ext_cap = cap;
+    const size_t slices = std::max<size_t>(Tcap, 4);  // K2: one slice per task; the sequential link step uses slice 0
+    H_CUDA(cudaMalloc(&sc.ext_keys, slices * cap * 8));
+    H_CUDA(cudaMalloc(&sc.ext_d, slices * cap * 4));
+    H_CUDA(cudaMalloc(&sc.ext_id, slices * cap * 4));
+    b.ext_keys = sc.ext_keys;
+    b.ext_d = sc.ext_d;
+    b.ext_id = sc.ext_id;
+  }
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, sc.req_key, sc.req_key2, sc.perm, sc.perm2, (int)req_cap, 0, 40,
                                   st);
@@ -756,7 +914,14 @@ int hnsw_insert_range(cozo_gpu_hnsw* h, uint32_t begin, uint32_t end, uint32_t m
     H_CUDA(cudaMemcpyAsync(&nreq, sc.counters + 1, 4, cudaMemcpyDeviceToHost, st));
     H_CUDA(cudaStreamSynchronize(st));
     if (nreq > req_cap) return set_error(COZO_GPU_ECUDA, "internal: in-edge queue overflow");
-    if (nreq) {
+    if (nreq && extend) {
+      // the reference links the selected neighbours one by one, nearest first (hnsw.rs:279-357); a later shrink sees
+      // the rows an earlier one left.  Requests sit in the queue in exactly that order (K2 writes a task's requests
+      // consecutively), so: one launch per request, in queue order, on this stream.
+      for (uint32_t r = 0; r < nreq; ++r)
+        k4<<<1, 32, smem4, st>>>(g, b, sc.req_key, sc.perm, sc.req_src, sc.req_d, nreq, sc.perm + r, 1);
+      H_CUDA(cudaGetLastError());
+    } else if (nreq) {
       size_t tb = cub_bytes;
       cub::DeviceRadixSort::SortPairs(sc.cub_tmp, tb, sc.req_key, sc.req_key2, sc.perm, sc.perm2, (int)nreq, 0, 40, st);
       build_heads_kernel<<<(nreq + 255) / 256, 256, 0, st>>>(sc.req_key2, nreq, sc.heads, sc.counters + 2);
@@ -839,7 +1004,6 @@ extern "C" int cozo_gpu_hnsw_build(cozo_gpu_hnsw_t** out, const CozoGpuHnswBuild
   if (d->m_neighbours < 2 || d->m_neighbours > 64)
     return set_error(COZO_GPU_EUNSUP, "m_neighbours must be in [2,64] for the device builder");
   if (d->ef_construction == 0) return set_error(COZO_GPU_EINVAL, "ef_construction must be set");  // sys.rs:603
-  if (d->extend_candidates) return set_error(COZO_GPU_EUNSUP, "extend_candidates is not supported by the device builder");
   if (d->n_vectors >= 0x7FFFFFFFu) return set_error(COZO_GPU_EUNSUP, "too many vectors");
   const uint32_t n = d->n_vectors;
   const uint32_t m = d->m_neighbours;
@@ -858,6 +1022,7 @@ extern "C" int cozo_gpu_hnsw_build(cozo_gpu_hnsw_t** out, const CozoGpuHnswBuild
   g.su = round_up(h->m_max, 32);
   h->ef_construction = d->ef_construction;
   h->keep_pruned = d->keep_pruned_connections;
+  h->extend_candidates = d->extend_candidates != 0;
   h->rng_state = d->level_seed;
   h->build_state_ready = true;
   auto fail = [&](int code) {
@@ -892,6 +1057,8 @@ extern "C" int cozo_gpu_hnsw_insert(cozo_gpu_hnsw_t* h, const float* vectors, ui
   if (ef_construction) h->ef_construction = ef_construction;
   if (h->ef_construction == 0) return set_error(COZO_GPU_EINVAL, "ef_construction must be set");
   if (keep_pruned_connections >= 0) h->keep_pruned = keep_pruned_connections;
+  // a staged handle learns the manifest's extend_candidates through the option (a built handle keeps its own)
+  if (get_option("hnsw.extend_candidates", -1) >= 0) h->extend_candidates = get_option("hnsw.extend_candidates", 0) != 0;
   rc = hnsw_ensure_build_state(h);
   if (rc) return rc;
   const uint32_t n0 = h->dev.n;

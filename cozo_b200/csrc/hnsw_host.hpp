@@ -54,6 +54,7 @@ struct cozo_gpu_hnsw {
   bool build_state_ready = false;
   uint32_t ef_construction = 0;
   int keep_pruned = 0;
+  int extend_candidates = 0;  // hnsw.rs:499-511: fidelity mode, one node per batch (hnsw_build.cu)
   uint64_t rng_state = 0x5EED0003ull;
   uint32_t n_live = 0;
   uint32_t borrowed_rows = 0;  // rows available in a borrowed vector buffer

@@ -1053,9 +1053,19 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
     if (smemA > di.smem_optin || smemB > di.smem_optin || smemF > di.smem_optin)
       return set_error(COZO_GPU_EUNSUP, "pagerank blocking does not fit shared memory (%zu / %zu / %zu of %zu bytes)", smemA,
                        smemB, smemF, di.smem_optin);
-    P_CUDA(cudaFuncSetAttribute(pb_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.smem_optin));
-    P_CUDA(cudaFuncSetAttribute(pb_accumulate_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.smem_optin));
-    P_CUDA(cudaFuncSetAttribute(pb_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.smem_optin));
+    // the dynamic limit is the opt-in maximum minus the kernel's static shared memory (never lowered per call)
+    auto raise_smem = [&](const void* fn, size_t need) -> int {
+      cudaFuncAttributes fa;
+      P_CUDA(cudaFuncGetAttributes(&fa, fn));
+      if (need + fa.sharedSizeBytes > di.smem_optin)
+        return set_error(COZO_GPU_EUNSUP, "pagerank blocking needs %zu + %zu B of shared memory (limit %zu)", need,
+                         (size_t)fa.sharedSizeBytes, di.smem_optin);
+      P_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(di.smem_optin - fa.sharedSizeBytes)));
+      return 0;
+    };
+    if ((rc = raise_smem((const void*)pb_gather_kernel, smemA)) != 0) return rc;
+    if ((rc = raise_smem((const void*)pb_accumulate_kernel<512>, smemB)) != 0) return rc;
+    if ((rc = raise_smem((const void*)pb_final_kernel, smemF)) != 0) return rc;
     int occB = 1, occF = 1;
     P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, pb_accumulate_kernel<512>, 512, smemB));
     P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, pb_final_kernel, KF_THREADS, smemF));

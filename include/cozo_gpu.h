@@ -171,7 +171,8 @@ typedef struct {
   int32_t borrow_vectors;       /* 1: keep using the caller's device buffer (must outlive the handle) */
   uint32_t m_neighbours;        /* m; m_max = m, m_max0 = 2m, level_multiplier = 1/ln m */
   uint32_t ef_construction;
-  int32_t extend_candidates;    /* must be 0 (COZO_GPU_EUNSUP otherwise) */
+  int32_t extend_candidates;    /* hnsw.rs:499-511.  Order-dependent: inserts one node per batch and links its
+                                   neighbours one at a time (the reference's sequential semantics); for small indexes */
   int32_t keep_pruned_connections;
   uint64_t level_seed;
   uint32_t max_batch;           /* 0 = default */

@@ -43,9 +43,43 @@ gg.sssp_paths(np.array([0, 5], np.uint32), np.array([7, 9], np.uint32), forb_nod
 hsrc = np.concatenate([np.arange(1, 6000), np.arange(2, 900), rng.integers(0, 6000, 4000)]).astype(np.uint32)
 hdst = np.concatenate([np.zeros(5999), np.ones(898), rng.integers(0, 6000, 4000)]).astype(np.uint32)
 hub = capi.Graph(6000, hsrc, hdst)
+capi.set_option("pagerank.mode", 0)                     # round-1 gather pull
 for warps in (32, 8):
     capi.set_option("pagerank.warps", warps)
     for dyn in (1, 0):
         capi.set_option("pagerank.dynamic", dyn)
         hub.pagerank(0.85, 0.0, 2)
+capi.set_option("pagerank.mode", 1)                     # propagation blocking: defaults and small geometries
+hub.pagerank(0.85, 0.0, 2)
+for nh, gs, win in ((64, 256, 512), (0, 64, 64), (1024, 4096, 3001)):
+    capi.set_option("pagerank.hub_slots", nh)
+    capi.set_option("pagerank.group_slots", gs)
+    capi.set_option("pagerank.window", win)
+    capi.set_option("pagerank.chunk", 1024)
+    hub.pagerank(0.85, 0.0, 2)
+    gg.pagerank(0.85, 1e-4, 3)
+# filter mask in every search mode, F64 index, the compacted-frontier SSSP, sharded operator at world size 1
+X = rng.random((1500, 48), dtype=np.float32)
+g = capi.HnswIndex.build(X, m=8, ef_construction=40)
+Q = rng.random((40, 48), dtype=np.float32)
+for mode in (1, 0, 2):
+    capi.set_option("hnsw.mode", mode)
+    g.search(Q, 5, 40, row_pass=rng.random(1500) < 0.3)
+capi.set_option("hnsw.mode", -1)
+ni, rp, ci, ep = g.export_levels()
+g64 = capi.HnswIndex.stage(X.astype(np.float64), ni, rp, ci, ep, m_max0=16, m_max=8)
+g64.search_f64(Q.astype(np.float64), 5, 40, row_pass=rng.random(1500) < 0.5)
+capi.set_option("sssp.force_queue", 1)
+gg.sssp(np.arange(0, 300, 50, dtype=np.uint32))
+gg.closeness()
+capi.set_option("sssp.force_queue", 0)
+for exch in (1, 0):
+    capi.set_option("shard.exchange", exch)
+    capi.set_option("shard.tile", 16)
+    grp = capi.ShardGroup(capi.ShardGroup.unique_id(), 0, 1)
+    grp.attach(g)
+    grp.search(Q, 5, 40)
+    grp.close()
+gx = capi.HnswIndex.build(X[:300], m=6, ef_construction=30, max_batch=1, extend_candidates=True)
+gx.search(Q, 5, 30)
 print("sanitize workload done")
