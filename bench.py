@@ -657,7 +657,7 @@ def main():
             gathered = [None] * world
             dist.all_gather_object(gathered, per)
             if rank == 0:
-                from tests.sharded_worker import numpy_merge
+                from cozo_b200.sharded import merge_lists as numpy_merge
                 offsets = np.arange(world, dtype=np.int64) * a.n
                 g_i, g_d = numpy_merge(np.stack([p[0] for p in gathered]), np.stack([p[1] for p in gathered]), offsets, k)
                 o_i, o_d = numpy_merge(np.stack([p[2] for p in gathered]), np.stack([p[3] for p in gathered]), offsets, k)

@@ -1,19 +1,27 @@
 """Row-sharded corpus: one process per GPU, one HNSW graph per shard.
 
-The query batch is replicated; every rank searches its own shard, the per-shard top-k
-lists are exchanged with ONE all-gather (NCCL over NVLink on the GPU box; gloo in the CPU
-tests of the plumbing) and merged on the device by cozo_gpu_topk_merge_dev.  The result is
-the k-NN over the union of the shards *as searched shard by shard* — parity is defined
-against the oracle run with the same sharding, not against a single big graph.
+The operator itself lives behind the C ABI (`cozo_gpu_shards_*`, `cozo_gpu_hnsw_stage_sharded`,
+`cozo_gpu_hnsw_search_sharded[_dev]` in csrc/sharded.cu; Python class `capi.ShardGroup`): query broadcast,
+per-shard search, exchange of the per-shard top-k lists (fused peer stores over CUDA IPC, or ONE NCCL
+all-gather per list) and the k-way merge all happen inside libcozo_gpu.so.
+
+What is left here is host-side plumbing that does not need a GPU and is covered by the world_size-2 gloo test:
+  * `ShardedTopK`  — shard offsets (row-contiguous partition) and the list exchange over any torch.distributed
+                     backend, i.e. the collective contract the library implements with NCCL;
+  * `merge_lists`  — the merge specification in numpy (what topk_merge_kernel computes);
+  * `make_group`   — rendezvous helper: rank 0 creates the 128-byte NCCL unique id, torch.distributed carries it.
+The result is the k-NN over the union of the shards *as searched shard by shard* — parity is defined against the
+oracle run with the same sharding, not against a single big graph.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
 
 class ShardedTopK:
-    """Collective plumbing shared by bench.py and the tests: shard offsets + list exchange."""
+    """Collective plumbing shared by the tests: shard offsets + list exchange."""
 
     def __init__(self, local_rows: int, device: torch.device, group=None):
         self.group = group
@@ -42,84 +50,30 @@ class ShardedTopK:
         return all_d, all_i
 
 
-class _PeerBuffers:
-    """[S,B,k] gather buffers in symmetric memory, double-buffered: every rank's search kernel
-    stores its lists straight into all peers' buffers over NVLink (fused exchange)."""
-
-    def __init__(self, world, B, k, device, group):
-        import torch.distributed._symmetric_memory as symm_mem
-        gname = group.group_name if group is not None else dist.group.WORLD.group_name
-        self.d, self.i, self.hd, self.hi = [], [], [], []
-        for _ in range(2):
-            td = symm_mem.empty((world, B, k), dtype=torch.float32, device=device)
-            ti = symm_mem.empty((world, B, k), dtype=torch.int32, device=device)
-            self.d.append(td)
-            self.i.append(ti)
-            self.hd.append(symm_mem.rendezvous(td, gname))
-            self.hi.append(symm_mem.rendezvous(ti, gname))
-        self.step = 0
+def merge_lists(all_ids: np.ndarray, all_dist: np.ndarray, offsets, k: int):
+    """[S,B,k] per-shard lists (local u32 ids, 0xFFFFFFFF padded, nearest first) -> global top-k:
+    ids u64 = offsets[s] + local id (UINT64_MAX padded), dist f32 (+inf padded); ties go to the lower shard."""
+    S, B, _ = all_ids.shape
+    out_i = np.full((B, k), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+    out_d = np.full((B, k), np.inf, np.float32)
+    for q in range(B):
+        cand = [(float(all_dist[s, q, j]), s, j, int(offsets[s]) + int(all_ids[s, q, j]))
+                for s in range(S) for j in range(all_ids.shape[2]) if all_ids[s, q, j] != 0xFFFFFFFF]
+        cand.sort(key=lambda t: (t[0], t[1], t[2]))
+        for r, c in enumerate(cand[:k]):
+            out_i[q, r] = c[3]
+            out_d[q, r] = c[0]
+    return out_i, out_d
 
 
-class ShardedHnswSearch:
-    """Device path (CUDA only, no CPU fallback).
-    exchange="nccl":  local search -> ONE NCCL all-gather per list -> merge kernel
-    exchange="fused": the search kernel's epilogue stores the lists into every peer's gather buffer
-                      (symmetric memory over NVLink), one device-side barrier, merge kernel."""
-
-    def __init__(self, index, local_rows: int, device: torch.device, group=None, exchange: str = "nccl"):
-        from . import capi
-        if device.type != "cuda":
-            raise capi.CozoGpuError(capi.E_NODEV, "ShardedHnswSearch needs a CUDA device (no CPU fallback)")
-        self.capi = capi
-        self.index = index
-        self.group = group
-        self.plumb = ShardedTopK(local_rows, device, group)
-        self.device = device
-        self.exchange = exchange if self.plumb.world > 1 else "nccl"
-        self._peer = {}
-
-    def _search_fused(self, q_dev, k, ef, qstats):
-        B = q_dev.shape[0]
-        key = (B, k)
-        if key not in self._peer:
-            # symmetric memory needs every peer to be NVLink/P2P reachable; agree on the outcome
-            try:
-                pb = _PeerBuffers(self.plumb.world, B, k, self.device, self.group)
-                ok = 1
-            except Exception as e:  # pragma: no cover - depends on the box
-                pb, ok = None, 0
-                self.fallback_reason = repr(e)
-            t = torch.tensor([ok], device=self.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
-            if int(t.item()) == 0:
-                self.exchange = "nccl"      # plain NCCL all-gather (the north-star exchange)
-                return self.search(q_dev, k, ef, qstats)
-            self._peer[key] = pb
-        pb = self._peer[key]
-        s = pb.step & 1
-        pb.step += 1
-        stream = torch.cuda.current_stream().cuda_stream
-        self.index.search_scatter_dev(q_dev.data_ptr(), B, k, ef, pb.hi[s].buffer_ptrs, pb.hd[s].buffer_ptrs,
-                                      self.plumb.rank, None if qstats is None else qstats.data_ptr(), stream)
-        pb.hd[s].barrier(channel=s)      # all ranks' stores have landed (and step-2's merge is long done)
-        out_i = torch.empty((B, k), dtype=torch.int64, device=self.device)
-        out_d = torch.empty((B, k), dtype=torch.float32, device=self.device)
-        self.capi.topk_merge_dev(pb.d[s].data_ptr(), pb.i[s].data_ptr(), self.plumb.world, B, k,
-                                 self.plumb.offsets.data_ptr(), out_i.data_ptr(), out_d.data_ptr(), stream)
-        return out_i, out_d
-
-    def search(self, q_dev: torch.Tensor, k: int, ef: int, qstats: torch.Tensor | None = None):
-        if self.exchange == "fused":
-            return self._search_fused(q_dev, k, ef, qstats)
-        B = q_dev.shape[0]
-        stream = torch.cuda.current_stream().cuda_stream
-        ids = torch.empty((B, k), dtype=torch.int32, device=self.device)
-        dd = torch.empty((B, k), dtype=torch.float32, device=self.device)
-        self.index.search_dev(q_dev.data_ptr(), B, k, ef, ids.data_ptr(), dd.data_ptr(), None,
-                              None if qstats is None else qstats.data_ptr(), stream)
-        all_d, all_i = self.plumb.gather(dd, ids)
-        out_i = torch.empty((B, k), dtype=torch.int64, device=self.device)
-        out_d = torch.empty((B, k), dtype=torch.float32, device=self.device)
-        self.capi.topk_merge_dev(all_d.data_ptr(), all_i.data_ptr(), self.plumb.world, B, k,
-                                 self.plumb.offsets.data_ptr(), out_i.data_ptr(), out_d.data_ptr(), stream)
-        return out_i, out_d
+def make_group(index, rank: int | None = None, world: int | None = None):
+    """collective: a capi.ShardGroup over the ranks of the default torch.distributed group, with `index` attached"""
+    from . import capi
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    uid = [capi.ShardGroup.unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    grp = capi.ShardGroup(uid[0], rank, world)
+    grp.attach(index)
+    return grp

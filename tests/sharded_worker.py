@@ -12,22 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def numpy_merge(all_ids, all_dist, offsets, k):
-    """[S,B,k] per-shard lists (local ids, NONE padded) -> global top-k by (dist, shard) like topk_merge_kernel"""
-    S, B, _ = all_ids.shape
-    out_i = np.full((B, k), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
-    out_d = np.full((B, k), np.inf, np.float32)
-    for q in range(B):
-        cand = []
-        for s in range(S):
-            for j in range(k):
-                if all_ids[s, q, j] != 0xFFFFFFFF:
-                    cand.append((float(all_dist[s, q, j]), s, j, int(offsets[s]) + int(all_ids[s, q, j])))
-        cand.sort(key=lambda t: (t[0], t[1], t[2]))
-        for r, c in enumerate(cand[:k]):
-            out_i[q, r] = c[3]
-            out_d[q, r] = c[0]
-    return out_i, out_d
+from cozo_b200.sharded import merge_lists as numpy_merge  # noqa: E402  (the merge specification)
 
 
 def main():

@@ -42,3 +42,14 @@ def test_two_rank_exchange(tmp_path):
     order = np.argsort(cat_d, axis=1, kind="stable")[:, :k]
     top = np.take_along_axis(cat_i, order, 1)
     assert top.shape == (B, k) and top.max() < 2234
+    # the merge specification the CUDA kernel is tested against (cozo_b200.sharded.merge_lists)
+    from cozo_b200.sharded import merge_lists
+    mi, md = merge_lists(r[0]["all_i"].astype(np.uint32), r[0]["all_d"], r[0]["offsets"], k)
+    assert np.array_equal(mi.astype(np.int64), top) and np.array_equal(md, np.take_along_axis(cat_d, order, 1))
+    # lists shorter than k (padding) never win a slot
+    ai = r[0]["all_i"].astype(np.uint32).copy()
+    ad = r[0]["all_d"].copy()
+    ai[1, :, 2:] = 0xFFFFFFFF
+    ad[1, :, 2:] = np.inf
+    mi2, md2 = merge_lists(ai, ad, r[0]["offsets"], k)
+    assert np.all(np.isfinite(md2)) and np.all(mi2 < 2234)
