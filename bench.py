@@ -76,6 +76,7 @@ def parse():
                     help="N>1: one NCCL all-gather per list (north star) or peer stores fused into the search kernel")
     ap.add_argument("--also-exchange", default=None, choices=["nccl", "fused"],
                     help="N>1: time the other exchange too on the same indexes (reported under `exchange_alt`)")
+    ap.add_argument("--device-gen", type=int, default=-1, help="1/0: generate the corpus in HBM / on the host (-1: HBM above 2M rows)")
     ap.add_argument("--out", default=None, help="--impl export-graph: where to write the graph")
     ap.add_argument("--scale", type=int, default=24, help="pagerank: RMAT scale")
     a = ap.parse_args()
@@ -441,7 +442,7 @@ def main():
         capi.set_option(name, int(val))
 
     # ---- corpus shard + index on this GPU -----------------------------------------------
-    on_device = a.n > 2_000_000            # big shards are generated in HBM (38 GB per shard at config 5)
+    on_device = a.n > 2_000_000 if a.device_gen < 0 else bool(a.device_gen)   # big shards are generated in HBM (38 GB at config 5)
     t0 = time.perf_counter()
     if on_device:
         Xd = gen_vectors_dev(a.n, a.dim, 0x5EED0001 + 1000 * rank, dev)

@@ -34,4 +34,24 @@ for name, (nn, s, d, ww) in {"air_routes(3476n,50637e)": (n, src, dst, w)}.items
                  "sssp_%d_sources" % srcs.size: {"gpu_kernel_ms": ms_s, "gpu_wall_ms": 1e3 * wall_s, "cpu_ms": 1e3 * cpu_s,
                                                  "dist_identical": bool(np.array_equal(gd, od))},
                  "cpu_threads": cores}
+# multi-source SSSP on R-MAT graphs that do not fit shared memory (compacted frontier queues): time per source next
+# to the 8E + 12N bytes-per-relaxation-pass model (a lower bound of ONE pass: a label-correcting search
+# makes several) and the oracle's Dijkstra on the host threads
+from tests.util import rmat_edges  # noqa: E402
+for scale in [int(x) for x in os.environ.get("COZO_BENCH_RMAT_SCALES", "18,20").split(",") if x]:
+    nn, s, d = rmat_edges(scale, 16, 0x5EED0004)
+    ww = (np.random.default_rng(scale).integers(1, 256, s.size) / 16.0).astype(np.float32)
+    g = capi.Graph(nn, s, d, ww)
+    o = O.OracleGraph(nn, s, d, ww)
+    srcs = np.arange(0, nn, nn // 64, dtype=np.uint32)[:64]
+    g.sssp(srcs[:2], want_pred=False)
+    t0 = time.perf_counter(); gd, _, ms_s = g.sssp(srcs, want_pred=False); wall_s = time.perf_counter() - t0
+    t0 = time.perf_counter(); od, _ = o.sssp(srcs, n_threads=cores); cpu_s = time.perf_counter() - t0
+    model = 8 * s.size + 12 * nn
+    out[f"rmat{scale}(n={nn},m={s.size})"] = {
+        "sssp_64_sources": {"gpu_kernel_ms": ms_s, "gpu_wall_ms": 1e3 * wall_s, "cpu_ms": 1e3 * cpu_s,
+                            "dist_identical": bool(np.array_equal(gd, od)), "ms_per_source": ms_s / 64,
+                            "one_pass_bytes_model": model,
+                            "one_pass_model_GBs_per_source": model / (ms_s / 64 / 1e3) / 1e9},
+        "cpu_threads": cores}
 print(json.dumps(out))

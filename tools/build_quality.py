@@ -14,7 +14,8 @@ from cozo_b200 import capi  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 capi.init(0)
-n, dim, m, efc = int(os.environ.get("BQ_N", 20000)), 768, 16, 100
+n, dim, m, efc = (int(os.environ.get("BQ_N", 20000)), int(os.environ.get("BQ_DIM", 768)), 16,
+                  int(os.environ.get("BQ_EFC", 100)))
 X = gen_vectors(n, dim, 7)
 Q = gen_vectors(500, dim, 8)
 t0 = time.perf_counter()

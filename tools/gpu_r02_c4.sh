@@ -17,6 +17,9 @@ for o in "pagerank.window=49152" "pagerank.window=12288" "pagerank.hub_slots=819
   timeout 300 python bench.py --workload pagerank --steps 3 --warmup 3 --no-cpu --opt $o 2>&1 | tail -c 900
 done > gpurun_out/c4/pagerank_sweep.txt 2>&1
 grep -E "sweep|ms_per_iteration" gpurun_out/c4/pagerank_sweep.txt | sed 's/.*"ms_per_iteration": \([0-9.]*\).*/  ms_per_iteration \1/'
+# pre-flight of the config-5 code path at toy size on one GPU (device-side generation, borrowed vectors, B > tile)
+timeout 600 python bench.py --workload config5 --rows 300000 --batch 200000 --device-gen 1 --steps 2 --warmup 1 > gpurun_out/c4/bench_config5_preflight.json 2> gpurun_out/c4/bench_config5_preflight.err
+tail -c 1200 gpurun_out/c4/bench_config5_preflight.json; tail -3 gpurun_out/c4/bench_config5_preflight.err
 # per-kernel times of one PageRank call
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pb_ --csv --log-file gpurun_out/c4/pagerank_launches.csv \
   python bench.py --workload pagerank --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
