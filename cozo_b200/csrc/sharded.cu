@@ -165,6 +165,15 @@ static int ensure_exchange(cozo_gpu_shards* s, uint32_t tile, uint32_t k) {
   tile = std::max(tile, s->tile_cap);
   k = std::max(k, s->k_cap);
   close_peers(s);
+  if (s->block && s->world > 1) {
+    // every rank has closed its mappings of the old blocks before any rank frees one (freeing exported memory
+    // that an importer still has open is undefined): one tiny all-gather as the rendezvous
+    uint32_t* d_tok = nullptr;
+    COZO_CUDA(cudaMalloc(&d_tok, 4 * (size_t)(s->world + 1)));
+    COZO_NCCL(g_nccl.AllGather(d_tok + s->world, d_tok, 1, ncclUint32, s->comm, s->stream));
+    COZO_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(d_tok);
+  }
   if (s->block) cudaFree(s->block);
   s->block = nullptr;
   for (int b = 0; b < 2; ++b) {
