@@ -990,7 +990,7 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   uint32_t launches = 0;
   PrArgs a{};
   PbArgs pb{};
-  uint32_t grid0 = 0, wpc = 32, gridA = 0, gridB = 0, gridF = 0;
+  uint32_t grid0 = 0, wpc = 32, gridA = 0, gridB = 0, gridF = 0, threadsB = 512;
   size_t smemA = 0, smemB = 0, smemF = 0;
   if (mode == 0) {
     P_CUDA(cudaMalloc(&partial.p, (size_t)std::max(st->n_chunks, 1u) * 4));
@@ -1064,10 +1064,15 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
       return 0;
     };
     if ((rc = raise_smem((const void*)pb_gather_kernel, smemA)) != 0) return rc;
-    if ((rc = raise_smem((const void*)pb_accumulate_kernel<512>, smemB)) != 0) return rc;
+    // a window above half of the shared memory leaves one CTA per SM: give it 32 warps instead of 16
+    const bool bigB = smemB > di.smem_optin / 2 || get_option("pagerank.accumulate_threads", 0) == 1024;
+    if ((rc = raise_smem(bigB ? (const void*)pb_accumulate_kernel<1024> : (const void*)pb_accumulate_kernel<512>, smemB)) != 0)
+      return rc;
     if ((rc = raise_smem((const void*)pb_final_kernel, smemF)) != 0) return rc;
     int occB = 1, occF = 1;
-    P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, pb_accumulate_kernel<512>, 512, smemB));
+    if (bigB) P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, pb_accumulate_kernel<1024>, 1024, smemB));
+    else P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, pb_accumulate_kernel<512>, 512, smemB));
+    threadsB = bigB ? 1024 : 512;
     P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, pb_final_kernel, KF_THREADS, smemF));
     if (occB < 1 || occF < 1) return set_error(COZO_GPU_ECUDA, "pagerank kernels do not fit on an SM");
     gridA = std::max(1u, std::min<uint32_t>(st->n_items, (uint32_t)di.sm_count));
@@ -1106,7 +1111,8 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
       pb.contrib_new = cnew;
       if (st->n_items) {
         pb_gather_kernel<<<gridA, 1024, smemA, sm>>>(pb);
-        pb_accumulate_kernel<512><<<gridB, 512, smemB, sm>>>(pb);
+        if (threadsB == 1024) pb_accumulate_kernel<1024><<<gridB, 1024, smemB, sm>>>(pb);
+        else pb_accumulate_kernel<512><<<gridB, 512, smemB, sm>>>(pb);
         pb_straddle_kernel<<<(st->NB + 255) / 256, 256, 0, sm>>>(pb);
         launches += 3;
       }
