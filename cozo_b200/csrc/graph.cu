@@ -204,16 +204,133 @@ __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ 
   }
 }
 
-// launch helper: shared-memory variant when the state fits
+// ---- "wide" form: few sources on a large graph --------------------------------------------------------------
+// One CTA per source leaves the device idle when a rule asks for one or a handful of start nodes on a big graph
+// (the common ShortestPathDijkstra call).  Here a ROUND is one launch of grid (ctas, n_src): all CTAs of a column
+// share the source's frontier queue (same layout as above), queue tails are device counters, the host reads the
+// n_src tail counts between rounds.  State is read with ld.global.cg (L2): the relaxing CTAs sit on different SMs.
+__global__ void sssp_wide_init_kernel(uint32_t n, const uint32_t* __restrict__ sources, uint32_t n_src,
+                                      unsigned long long* state, uint8_t* flags, size_t flags_stride, uint32_t* counts) {
+  const uint32_t si = blockIdx.y;
+  unsigned long long* st = state + (size_t)si * n;
+  uint8_t* fb = flags + (size_t)si * flags_stride;
+  uint32_t* qa = reinterpret_cast<uint32_t*>(fb);
+  uint8_t* queued = reinterpret_cast<uint8_t*>(qa + 2 * (size_t)n);
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    st[v] = v == sources[si] ? 0x00000000FFFFFFFFull : SSSP_INF;
+    queued[v] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    qa[0] = sources[si];
+    counts[si] = 1;           // current frontier
+    counts[n_src + si] = 0;   // next frontier
+  }
+}
+
+template <bool FORB>
+__global__ void __launch_bounds__(256) sssp_wide_round_kernel(const uint32_t* __restrict__ out_ptr,
+                                                              const uint32_t* __restrict__ out_idx,
+                                                              const float* __restrict__ out_w, uint32_t n, uint32_t n_src,
+                                                              unsigned long long* state, uint8_t* flags,
+                                                              size_t flags_stride, uint32_t* counts, uint32_t parity,
+                                                              ForbiddenSets fs) {
+  const uint32_t si = blockIdx.y;
+  const uint32_t count = counts[parity * n_src + si];
+  if (count == 0) return;
+  uint32_t* tail = counts + (parity ^ 1u) * n_src + si;
+  unsigned long long* st = state + (size_t)si * n;
+  uint8_t* fb = flags + (size_t)si * flags_stride;
+  uint32_t* q0 = reinterpret_cast<uint32_t*>(fb);
+  uint32_t* qa = q0 + (size_t)parity * n;
+  uint32_t* qb = q0 + (size_t)(parity ^ 1u) * n;
+  uint8_t* queued = reinterpret_cast<uint8_t*>(q0 + 2 * (size_t)n);
+  uint32_t fnb = 0, fne = 0, feb = 0, fee = 0;
+  if (FORB) {
+    fnb = fs.fn_ptr[si];
+    fne = fs.fn_ptr[si + 1];
+    feb = fs.fe_ptr[si];
+    fee = fs.fe_ptr[si + 1];
+  }
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpb = blockDim.x >> 5;
+  for (uint32_t i = blockIdx.x * wpb + (threadIdx.x >> 5); i < count; i += gridDim.x * wpb) {
+    const uint32_t u = qa[i];
+    if (lane == 0) {
+      atomicAnd(reinterpret_cast<uint32_t*>(queued + (u & ~3u)), ~(0xFFu << (8 * (u & 3u))));
+      __threadfence();  // the clear is ordered before the read of u's distance below
+    }
+    __syncwarp();
+    const float du = __uint_as_float((uint32_t)(__ldcg(st + u) >> 32));
+    const uint32_t kb = out_ptr[u], ke = out_ptr[u + 1];
+    for (uint32_t k = kb + lane; k < ke; k += 32) {
+      const uint32_t v = out_idx[k];
+      if (FORB) {
+        bool skip = false;
+        for (uint32_t f = fnb; f < fne; ++f) skip |= fs.fn_nodes[f] == v;
+        for (uint32_t f = feb; f < fee; ++f) skip |= (fs.fe_src[f] == u) & (fs.fe_dst[f] == v);
+        if (skip) continue;
+      }
+      const float nd = du + (out_w ? out_w[k] : 1.0f);
+      unsigned long long old = __ldcg(st + v);
+      while (nd < __uint_as_float((uint32_t)(old >> 32))) {
+        const unsigned long long want = ((unsigned long long)__float_as_uint(nd) << 32) | u;
+        const unsigned long long got = atomicCAS(&st[v], old, want);
+        if (got == old) {
+          __threadfence();  // the new distance is visible before the node can be seen as queued
+          uint32_t* wp = reinterpret_cast<uint32_t*>(queued + (v & ~3u));
+          const uint32_t bit = 1u << (8 * (v & 3u));
+          if (!(atomicOr(wp, bit) & bit)) qb[atomicAdd(tail, 1u)] = v;
+          break;
+        }
+        old = got;
+      }
+    }
+  }
+}
+__global__ void sssp_wide_reset_kernel(uint32_t* counts, uint32_t n_src, uint32_t parity) {
+  const uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+  if (si < n_src) counts[parity * n_src + si] = 0;
+}
+
+// launch helper: shared-memory form when the state fits, the wide form for few sources on a large graph, else one
+// CTA per source with frontier queues.  The wide form loops on the host (one small readback per round).
 static size_t sssp_flags_stride(uint32_t n) { return ((size_t)n * 9 + 15) & ~(size_t)15; }
 template <bool FORB>
 static cudaError_t launch_sssp(cozo_gpu_graph_t* g, const uint32_t* d_sources, uint32_t n_src,
                                unsigned long long* state, uint8_t* flags, ForbiddenSets fs, cudaStream_t st) {
   const uint32_t n = g->n;
   const size_t need = (size_t)n * 10;
-  if (need + 1024 <= device_info().smem_optin && !get_option("sssp.force_queue", 0)) {
+  const DeviceInfo& di = device_info();
+  const int64_t wide_opt = get_option("sssp.wide", -1);
+  const bool fits = need + 1024 <= di.smem_optin && !get_option("sssp.force_queue", 0);
+  const bool wide = wide_opt >= 0 ? wide_opt != 0 : (!fits && n_src * 2 <= (uint32_t)di.sm_count && g->m >= (1u << 20));
+  if (wide) {
+    uint32_t* counts = nullptr;
+    cudaError_t e = cudaMalloc(&counts, (size_t)2 * n_src * 4);
+    if (e != cudaSuccess) return e;
+    const uint32_t ctas = std::max<uint32_t>(1, (uint32_t)di.sm_count * 4 / n_src);
+    sssp_wide_init_kernel<<<dim3(std::min<uint32_t>(ctas, (n + 255) / 256), n_src), 256, 0, st>>>(
+        n, d_sources, n_src, state, flags, sssp_flags_stride(n), counts);
+    std::vector<uint32_t> h(n_src);
+    uint32_t parity = 0;
+    for (;;) {
+      sssp_wide_round_kernel<FORB><<<dim3(ctas, n_src), 256, 0, st>>>(g->out_ptr, g->out_idx, g->out_w, n, n_src, state, flags,
+                                                                     sssp_flags_stride(n), counts, parity, fs);
+      sssp_wide_reset_kernel<<<(n_src + 255) / 256, 256, 0, st>>>(counts, n_src, parity);  // consumed: next "next"
+      parity ^= 1u;
+      e = cudaMemcpyAsync(h.data(), counts + (size_t)parity * n_src, (size_t)n_src * 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) break;
+      bool any = false;
+      for (uint32_t c : h) any |= c != 0;
+      if (!any) break;
+    }
+    cudaFree(counts);
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
+  if (fits) {
     cudaError_t e = cudaFuncSetAttribute(sssp_kernel<FORB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)device_info().smem_optin);
+                                         (int)di.smem_optin);
     if (e != cudaSuccess) return e;
     sssp_kernel<FORB, true><<<n_src, 256, need, st>>>(g->out_ptr, g->out_idx, g->out_w, n, d_sources, n_src, state, flags,
                                                       sssp_flags_stride(n), fs);

@@ -253,6 +253,16 @@ def test_sssp_queue_frontier_and_large_graph(gpu):
     gd, gp, _ = g2.sssp(srcs)
     od, _ = o2.sssp(srcs, n_threads=8)
     assert np.array_equal(gd, od)
+    # few sources on a large graph: the "wide" form (many CTAs per source, one launch per round)
+    gpu.set_option("sssp.wide", 1)
+    try:
+        gw, pw, _ = g2.sssp(srcs[:3])
+        assert np.array_equal(gw, od[:3])
+        _check_tree(s2, d2, w2, srcs[:1], gw[:1], pw[:1], n)
+        g1 = gpu.Graph(500, src, dst, w)
+        assert np.array_equal(g1.sssp(sources)[0], O.OracleGraph(500, src, dst, w).sssp(sources, n_threads=8)[0])
+    finally:
+        gpu.set_option("sssp.wide", -1)
 
 
 def test_betweenness_is_deterministic_and_rejects_zero_weight_cycles(gpu):
@@ -342,6 +352,12 @@ def test_sssp_paths_with_forbidden_sets(gpu):
     fn = [[int(x) for x in rng.integers(0, n, rng.integers(0, 4)) if x != sources[i]] for i in range(40)]
     fe = [[pairs[int(j)] for j in rng.integers(0, len(pairs), rng.integers(0, 5))] for i in range(40)]
     res, _ = g.sssp_paths(sources, goals, fn, fe, max_len=4)        # small buffer: exercises the retry
+    for opt in ("sssp.force_queue", "sssp.wide"):                    # the other two frontier forms: same answers
+        gpu.set_option(opt, 1)
+        try:
+            assert g.sssp_paths(sources, goals, fn, fe, max_len=64)[0] == res
+        finally:
+            gpu.set_option(opt, -1 if opt == "sssp.wide" else 0)
     for i in range(40):
         keep = np.array([(a, b) not in set(fe[i]) and b not in set(fn[i]) for a, b in pairs])
         o = O.OracleGraph(n, src[keep], dst[keep], w[keep])

@@ -73,6 +73,10 @@ capi.set_option("sssp.force_queue", 1)
 gg.sssp(np.arange(0, 300, 50, dtype=np.uint32))
 gg.closeness()
 capi.set_option("sssp.force_queue", 0)
+capi.set_option("sssp.wide", 1)
+gg.sssp(np.arange(0, 300, 100, dtype=np.uint32))
+gg.sssp_paths(np.array([0, 5], np.uint32), np.array([7, 9], np.uint32), forb_nodes=[[3], []], forb_edges=[[], [(5, 9)]])
+capi.set_option("sssp.wide", -1)
 for exch in (1, 0):
     capi.set_option("shard.exchange", exch)
     capi.set_option("shard.tile", 16)
