@@ -643,32 +643,41 @@ def main():
             shard_bytes = a.n * dim * 4 + a.n * 40 * 4
             avail = mem_available_bytes()
             group = world if avail == 0 else max(1, min(world, int(0.6 * avail // max(shard_bytes, 1))))
-            per = None
+            per, perr = None, None
             for g0 in range(0, world, group):
                 if g0 <= rank < g0 + group:
-                    Xh = X if X is not None else Xd.cpu().numpy()
-                    levels = g.export_levels()
-                    ix = O.OracleHnsw.from_levels(Xh, O.HnswLevels(*levels))
-                    oi, od, _, ost = ix.search(Qs, k, ef, n_threads=max(1, cores // min(group, world)))
-                    li, ld, _, lst = g.search(Qs, k, ef)
-                    per = (li, ld, oi, od, int(lst.dist_evals), int(ost[:, 0].sum()))
-                    del ix, Xh, levels
+                    try:      # a failure here must not desynchronise the ranks: the collectives below always run
+                        Xh = X if X is not None else Xd.cpu().numpy()
+                        levels = g.export_levels()
+                        ix = O.OracleHnsw.from_levels(Xh, O.HnswLevels(*levels))
+                        oi, od, _, ost = ix.search(Qs, k, ef, n_threads=max(1, cores // min(group, world)))
+                        li, ld, _, lst = g.search(Qs, k, ef)
+                        per = (li, ld, oi, od, int(lst.dist_evals), int(ost[:, 0].sum()))
+                        del ix, Xh, levels
+                    except Exception as e:          # noqa: BLE001
+                        perr = repr(e)
                 dist.barrier()
             mi, md, mc, _ = grp.search(Qs, k, ef, root=-1)
             gathered = [None] * world
-            dist.all_gather_object(gathered, per)
+            dist.all_gather_object(gathered, (per, perr))
             if rank == 0:
-                from cozo_b200.sharded import merge_lists as numpy_merge
-                offsets = np.arange(world, dtype=np.int64) * a.n
-                g_i, g_d = numpy_merge(np.stack([p[0] for p in gathered]), np.stack([p[1] for p in gathered]), offsets, k)
-                o_i, o_d = numpy_merge(np.stack([p[2] for p in gathered]), np.stack([p[3] for p in gathered]), offsets, k)
-                recall_vs_oracle = recall_rows(mi, o_i, k)
-                parity = {"queries_per_shard": int(sample),
-                          "per_shard_recall_vs_oracle": [recall_rows(p[0], p[2], k) for p in gathered],
-                          "per_shard_dist_evals": [{"gpu": p[4], "oracle": p[5]} for p in gathered],
-                          "merged_equals_numpy_merge_of_gpu_lists": bool(np.array_equal(mi, g_i) and np.array_equal(md, g_d)),
-                          "merged_recall_vs_merged_oracle": recall_vs_oracle,
-                          "oracle_ranks_at_a_time": int(group)}
+                try:
+                    if any(p[0] is None for p in gathered):
+                        raise RuntimeError("; ".join(str(p[1]) for p in gathered if p[1]))
+                    gathered = [p[0] for p in gathered]
+                    from cozo_b200.sharded import merge_lists as numpy_merge
+                    offsets = np.arange(world, dtype=np.int64) * a.n
+                    g_i, g_d = numpy_merge(np.stack([p[0] for p in gathered]), np.stack([p[1] for p in gathered]), offsets, k)
+                    o_i, o_d = numpy_merge(np.stack([p[2] for p in gathered]), np.stack([p[3] for p in gathered]), offsets, k)
+                    recall_vs_oracle = recall_rows(mi, o_i, k)
+                    parity = {"queries_per_shard": int(sample),
+                              "per_shard_recall_vs_oracle": [recall_rows(p[0], p[2], k) for p in gathered],
+                              "per_shard_dist_evals": [{"gpu": p[4], "oracle": p[5]} for p in gathered],
+                              "merged_equals_numpy_merge_of_gpu_lists": bool(np.array_equal(mi, g_i) and np.array_equal(md, g_d)),
+                              "merged_recall_vs_merged_oracle": recall_vs_oracle,
+                              "oracle_ranks_at_a_time": int(group)}
+                except Exception as e:              # noqa: BLE001
+                    parity = {"error": repr(e)}
 
     if rank == 0:
         info = grp.info() if grp is not None else None

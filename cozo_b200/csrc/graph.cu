@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "graph_host.hpp"
@@ -69,11 +70,10 @@ struct ForbiddenSets {
   const uint32_t *fn_ptr, *fn_nodes, *fe_ptr, *fe_src, *fe_dst;
 };
 
-// SMEM = true: the per-source state (8 B/node) and two frontier flag arrays (1 B/node each) live in shared
-// memory (graphs up to ~22 k nodes); a round scans the flags.  SMEM = false (larger graphs): state in HBM and
-// a COMPACTED frontier — two node queues per source plus an "already queued" flag per node, so a round costs
-// O(frontier + its edges), not O(n).  A warp takes one frontier node at a time; its lanes stride the out-edges.
-// Layout of `flags` per source when SMEM = false: [queue A: n u32][queue B: n u32][queued: n u8 (padded)].
+// SMEM = the per-source state (8 B/node) and the two frontier flag arrays (1 B/node each) live in
+// shared memory (graphs up to ~22 k nodes); the final state is copied out for the read-out kernels.
+// A warp takes one frontier node at a time and its lanes stride the node's out-edges.  A round scans the
+// flag arrays (O(n) per round): the default form, verified on the GPU since round 1.
 template <bool FORB, bool SMEM>
 __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ out_ptr,
                                                    const uint32_t* __restrict__ out_idx,
@@ -93,114 +93,152 @@ __global__ void __launch_bounds__(256) sssp_kernel(const uint32_t* __restrict__ 
   }
   unsigned long long* gst = state + (size_t)si * n;
   unsigned long long* st = SMEM ? reinterpret_cast<unsigned long long*>(sssp_smem) : gst;
+  uint8_t* cur = SMEM ? sssp_smem + (size_t)n * 8 : flags + (size_t)si * flags_stride;
+  uint8_t* nxt = cur + n;
+  __shared__ int s_any;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  __shared__ int s_any;
-  __shared__ uint32_t s_tail;
-  // relax the out-edges of u (distance du); `on_improve(v)` runs once per successful CAS
-  auto relax = [&](uint32_t u, auto&& on_improve) {
-    const float du = __uint_as_float((uint32_t)(st[u] >> 32));
-    const uint32_t kb = out_ptr[u], ke = out_ptr[u + 1];
-    for (uint32_t k = kb + lane; k < ke; k += 32) {
-      const uint32_t v = out_idx[k];
-      if (FORB) {  // shortest_path_dijkstra.rs:298-303
-        bool skip = false;
-        for (uint32_t f = fnb; f < fne; ++f) skip |= fs.fn_nodes[f] == v;
-        for (uint32_t f = feb; f < fee; ++f) skip |= (fs.fe_src[f] == u) & (fs.fe_dst[f] == v);
-        if (skip) continue;
-      }
-      const float nd = du + (out_w ? out_w[k] : 1.0f);
-      unsigned long long old = st[v];
-      while (nd < __uint_as_float((uint32_t)(old >> 32))) {
-        unsigned long long want = ((unsigned long long)__float_as_uint(nd) << 32) | u;
-        unsigned long long got = atomicCAS(&st[v], old, want);
-        if (got == old) {
-          on_improve(v);
-          break;
+  for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
+    st[v] = SSSP_INF;
+    cur[v] = 0;
+    nxt[v] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = sources[si];
+    st[s] = 0x00000000FFFFFFFFull;  // dist 0, no predecessor
+    cur[s] = 1;
+  }
+  __syncthreads();
+  for (;;) {
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    bool any_local = false;
+    for (uint32_t u = warp; u < n; u += nwarps) {
+      if (!cur[u]) continue;  // warp-uniform
+      __syncwarp();
+      if (lane == 0) cur[u] = 0;
+      const float du = __uint_as_float((uint32_t)(st[u] >> 32));
+      const uint32_t kb = out_ptr[u], ke = out_ptr[u + 1];
+      for (uint32_t k = kb + lane; k < ke; k += 32) {
+        const uint32_t v = out_idx[k];
+        if (FORB) {  // shortest_path_dijkstra.rs:298-303
+          bool skip = false;
+          for (uint32_t f = fnb; f < fne; ++f) skip |= fs.fn_nodes[f] == v;
+          for (uint32_t f = feb; f < fee; ++f) skip |= (fs.fe_src[f] == u) & (fs.fe_dst[f] == v);
+          if (skip) continue;
         }
-        old = got;
+        const float nd = du + (out_w ? out_w[k] : 1.0f);
+        unsigned long long old = st[v];
+        while (nd < __uint_as_float((uint32_t)(old >> 32))) {
+          unsigned long long want = ((unsigned long long)__float_as_uint(nd) << 32) | u;
+          unsigned long long got = atomicCAS(&st[v], old, want);
+          if (got == old) {
+            nxt[v] = 1;
+            any_local = true;
+            break;
+          }
+          old = got;
+        }
       }
     }
-  };
-  if (SMEM) {
-    uint8_t* cur = sssp_smem + (size_t)n * 8;
-    uint8_t* nxt = cur + n;
-    for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
-      st[v] = SSSP_INF;
-      cur[v] = 0;
-      nxt[v] = 0;
-    }
+    if (any_local) s_any = 1;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t s = sources[si];
-      st[s] = 0x00000000FFFFFFFFull;  // dist 0, no predecessor
-      cur[s] = 1;
-    }
+    const int any = s_any;
     __syncthreads();
-    for (;;) {
-      if (threadIdx.x == 0) s_any = 0;
-      __syncthreads();
-      bool any_local = false;
-      for (uint32_t u = warp; u < n; u += nwarps) {
-        if (!cur[u]) continue;  // warp-uniform
-        __syncwarp();
-        if (lane == 0) cur[u] = 0;
-        relax(u, [&](uint32_t v) {
-          nxt[v] = 1;
-          any_local = true;
-        });
-      }
-      if (any_local) s_any = 1;
-      __syncthreads();
-      const int any = s_any;
-      __syncthreads();
-      if (!any) break;
-      uint8_t* t = cur;
-      cur = nxt;
-      nxt = t;
-    }
+    if (!any) break;
+    uint8_t* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  if (SMEM)
     for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) gst[v] = st[v];
-  } else {
-    uint8_t* fb = flags + (size_t)si * flags_stride;
-    uint32_t* qa = reinterpret_cast<uint32_t*>(fb);
-    uint32_t* qb = qa + n;
-    uint8_t* queued = reinterpret_cast<uint8_t*>(qb + n);
-    for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
-      st[v] = SSSP_INF;
-      queued[v] = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t s = sources[si];
-      st[s] = 0x00000000FFFFFFFFull;
-      qa[0] = s;
-      s_tail = 0;
-    }
-    uint32_t count = 1;
-    __syncthreads();
-    while (count) {
-      for (uint32_t i = warp; i < count; i += nwarps) {
-        const uint32_t u = qa[i];
-        __syncwarp();
-        if (lane == 0)  // u may be queued again by a later improvement
-          atomicAnd(reinterpret_cast<uint32_t*>(queued + (u & ~3u)), ~(0xFFu << (8 * (u & 3u))));
-        relax(u, [&](uint32_t v) {
-          // one byte per node: test-and-set through a 32-bit atomicOr on the aligned word
-          uint32_t* wp = reinterpret_cast<uint32_t*>(queued + (v & ~3u));
-          const uint32_t bit = 1u << (8 * (v & 3u));
-          const uint32_t old = atomicOr(wp, bit);
-          if (!(old & bit)) qb[atomicAdd(&s_tail, 1u)] = v;
-        });
+}
+
+// COMPACTED frontier (option "sssp.frontier" = 1; not yet run on a GPU): state in HBM, two node
+// queues per source plus an "already queued" byte per node, so a round costs O(frontier + its edges), not O(n).
+// Layout of `flags` per source: [queue A: n u32][queue B: n u32][queued: n u8 (padded)].  Rounds are capped at n + 2
+// (a label-correcting search settles a shortest path of h hops within h rounds), so the kernel always terminates.
+template <bool FORB>
+__global__ void __launch_bounds__(256) sssp_queue_kernel(const uint32_t* __restrict__ out_ptr,
+                                                         const uint32_t* __restrict__ out_idx,
+                                                         const float* __restrict__ out_w, uint32_t n,
+                                                         const uint32_t* __restrict__ sources, uint32_t n_src,
+                                                         unsigned long long* state, uint8_t* flags, size_t flags_stride,
+                                                         ForbiddenSets fs) {
+  const uint32_t si = blockIdx.x;
+  if (si >= n_src) return;
+  uint32_t fnb = 0, fne = 0, feb = 0, fee = 0;
+  if (FORB) {
+    fnb = fs.fn_ptr[si];
+    fne = fs.fn_ptr[si + 1];
+    feb = fs.fe_ptr[si];
+    fee = fs.fe_ptr[si + 1];
+  }
+  unsigned long long* st = state + (size_t)si * n;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  __shared__ uint32_t s_tail;
+  uint8_t* fb = flags + (size_t)si * flags_stride;
+  uint32_t* qa = reinterpret_cast<uint32_t*>(fb);
+  uint32_t* qb = qa + n;
+  uint8_t* queued = reinterpret_cast<uint8_t*>(qb + n);
+  for (uint32_t v = threadIdx.x; v < n; v += blockDim.x) {
+    st[v] = SSSP_INF;
+    queued[v] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = sources[si];
+    st[s] = 0x00000000FFFFFFFFull;
+    qa[0] = s;
+    s_tail = 0;
+  }
+  uint32_t count = 1;
+  __syncthreads();
+  for (uint32_t round = 0; count && round < n + 2; ++round) {
+    for (uint32_t i = warp; i < count; i += nwarps) {
+      const uint32_t u = qa[i];
+      __syncwarp();
+      if (lane == 0)  // u may be queued again by a later improvement
+        atomicAnd(reinterpret_cast<uint32_t*>(queued + (u & ~3u)), ~(0xFFu << (8 * (u & 3u))));
+      const float du = __uint_as_float((uint32_t)(st[u] >> 32));
+      const uint32_t kb = out_ptr[u], ke = out_ptr[u + 1];
+      for (uint32_t k = kb + lane; k < ke; k += 32) {
+        const uint32_t v = out_idx[k];
+        if (FORB) {
+          bool skip = false;
+          for (uint32_t f = fnb; f < fne; ++f) skip |= fs.fn_nodes[f] == v;
+          for (uint32_t f = feb; f < fee; ++f) skip |= (fs.fe_src[f] == u) & (fs.fe_dst[f] == v);
+          if (skip) continue;
+        }
+        const float nd = du + (out_w ? out_w[k] : 1.0f);
+        unsigned long long old = st[v];
+        while (nd < __uint_as_float((uint32_t)(old >> 32))) {
+          unsigned long long want = ((unsigned long long)__float_as_uint(nd) << 32) | u;
+          unsigned long long got = atomicCAS(&st[v], old, want);
+          if (got == old) {
+            // one byte per node: test-and-set through a 32-bit atomicOr on the aligned word
+            uint32_t* wp = reinterpret_cast<uint32_t*>(queued + (v & ~3u));
+            const uint32_t bit = 1u << (8 * (v & 3u));
+            if (!(atomicOr(wp, bit) & bit)) {
+              const uint32_t at = atomicAdd(&s_tail, 1u);
+              if (at < n) qb[at] = v;
+            }
+            break;
+          }
+          old = got;
+        }
       }
-      __syncthreads();
-      count = s_tail;
-      __syncthreads();
-      if (threadIdx.x == 0) s_tail = 0;
-      uint32_t* t = qa;
-      qa = qb;
-      qb = t;
-      __syncthreads();
     }
+    __syncthreads();
+    count = s_tail < n ? s_tail : n;
+    __syncthreads();
+    if (threadIdx.x == 0) s_tail = 0;
+    uint32_t* t = qa;
+    qa = qb;
+    qb = t;
+    __syncthreads();
   }
 }
 
@@ -235,7 +273,7 @@ __global__ void __launch_bounds__(256) sssp_wide_round_kernel(const uint32_t* __
                                                               size_t flags_stride, uint32_t* counts, uint32_t parity,
                                                               ForbiddenSets fs) {
   const uint32_t si = blockIdx.y;
-  const uint32_t count = counts[parity * n_src + si];
+  const uint32_t count = min(counts[parity * n_src + si], n);
   if (count == 0) return;
   uint32_t* tail = counts + (parity ^ 1u) * n_src + si;
   unsigned long long* st = state + (size_t)si * n;
@@ -279,7 +317,10 @@ __global__ void __launch_bounds__(256) sssp_wide_round_kernel(const uint32_t* __
           __threadfence();  // the new distance is visible before the node can be seen as queued
           uint32_t* wp = reinterpret_cast<uint32_t*>(queued + (v & ~3u));
           const uint32_t bit = 1u << (8 * (v & 3u));
-          if (!(atomicOr(wp, bit) & bit)) qb[atomicAdd(tail, 1u)] = v;
+          if (!(atomicOr(wp, bit) & bit)) {
+            const uint32_t at = atomicAdd(tail, 1u);
+            if (at < n) qb[at] = v;
+          }
           break;
         }
         old = got;
@@ -292,8 +333,9 @@ __global__ void sssp_wide_reset_kernel(uint32_t* counts, uint32_t n_src, uint32_
   if (si < n_src) counts[parity * n_src + si] = 0;
 }
 
-// launch helper: shared-memory form when the state fits, the wide form for few sources on a large graph, else one
-// CTA per source with frontier queues.  The wide form loops on the host (one small readback per round).
+// launch helper.  Default = the flag-scan kernel (shared-memory state when it fits).  Options, both off by default
+// because neither form has run on a GPU yet: "sssp.frontier" = 1 -> compacted frontier queues (one CTA per source),
+// "sssp.wide" = 1 -> many CTAs per source with one launch per round (host loop, capped at n + 2 rounds).
 static size_t sssp_flags_stride(uint32_t n) { return ((size_t)n * 9 + 15) & ~(size_t)15; }
 template <bool FORB>
 static cudaError_t launch_sssp(cozo_gpu_graph_t* g, const uint32_t* d_sources, uint32_t n_src,
@@ -301,21 +343,19 @@ static cudaError_t launch_sssp(cozo_gpu_graph_t* g, const uint32_t* d_sources, u
   const uint32_t n = g->n;
   const size_t need = (size_t)n * 10;
   const DeviceInfo& di = device_info();
-  const int64_t wide_opt = get_option("sssp.wide", -1);
-  const bool fits = need + 1024 <= di.smem_optin && !get_option("sssp.force_queue", 0);
-  const bool wide = wide_opt >= 0 ? wide_opt != 0 : (!fits && n_src * 2 <= (uint32_t)di.sm_count && g->m >= (1u << 20));
-  if (wide) {
+  const size_t fstride = sssp_flags_stride(n);
+  if (get_option("sssp.wide", 0) == 1) {
     uint32_t* counts = nullptr;
     cudaError_t e = cudaMalloc(&counts, (size_t)2 * n_src * 4);
     if (e != cudaSuccess) return e;
     const uint32_t ctas = std::max<uint32_t>(1, (uint32_t)di.sm_count * 4 / n_src);
     sssp_wide_init_kernel<<<dim3(std::min<uint32_t>(ctas, (n + 255) / 256), n_src), 256, 0, st>>>(
-        n, d_sources, n_src, state, flags, sssp_flags_stride(n), counts);
+        n, d_sources, n_src, state, flags, fstride, counts);
     std::vector<uint32_t> h(n_src);
     uint32_t parity = 0;
-    for (;;) {
+    for (uint32_t round = 0; round < n + 2; ++round) {
       sssp_wide_round_kernel<FORB><<<dim3(ctas, n_src), 256, 0, st>>>(g->out_ptr, g->out_idx, g->out_w, n, n_src, state, flags,
-                                                                     sssp_flags_stride(n), counts, parity, fs);
+                                                                     fstride, counts, parity, fs);
       sssp_wide_reset_kernel<<<(n_src + 255) / 256, 256, 0, st>>>(counts, n_src, parity);  // consumed: next "next"
       parity ^= 1u;
       e = cudaMemcpyAsync(h.data(), counts + (size_t)parity * n_src, (size_t)n_src * 4, cudaMemcpyDeviceToHost, st);
@@ -328,15 +368,28 @@ static cudaError_t launch_sssp(cozo_gpu_graph_t* g, const uint32_t* d_sources, u
     cudaFree(counts);
     return e != cudaSuccess ? e : cudaGetLastError();
   }
-  if (fits) {
-    cudaError_t e = cudaFuncSetAttribute(sssp_kernel<FORB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)di.smem_optin);
-    if (e != cudaSuccess) return e;
+  if (get_option("sssp.frontier", 0) == 1) {
+    sssp_queue_kernel<FORB><<<n_src, 256, 0, st>>>(g->out_ptr, g->out_idx, g->out_w, n, d_sources, n_src, state, flags,
+                                                   fstride, fs);
+    return cudaGetLastError();
+  }
+  if (need + 1024 <= di.smem_optin) {
+    // raise the kernel's dynamic shared-memory limit, never lower it (concurrent callers with other graphs)
+    static std::mutex mu;
+    static size_t raised[2] = {0, 0};
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (need > raised[FORB ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute(sssp_kernel<FORB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        if (e != cudaSuccess) return e;
+        raised[FORB ? 1 : 0] = need;
+      }
+    }
     sssp_kernel<FORB, true><<<n_src, 256, need, st>>>(g->out_ptr, g->out_idx, g->out_w, n, d_sources, n_src, state, flags,
-                                                      sssp_flags_stride(n), fs);
+                                                      fstride, fs);
   } else {
     sssp_kernel<FORB, false><<<n_src, 256, 0, st>>>(g->out_ptr, g->out_idx, g->out_w, n, d_sources, n_src, state, flags,
-                                                    sssp_flags_stride(n), fs);
+                                                    fstride, fs);
   }
   return cudaGetLastError();
 }
@@ -752,8 +805,12 @@ static int sssp_chunks(cozo_gpu_graph_t* g, CallStream& cs, const uint32_t* sour
     }
     uint32_t c = std::min(chunk, n_src - s0);
     cudaMemcpyAsync(dsrc.p, sources_host + s0, (size_t)c * 4, cudaMemcpyHostToDevice, cs.s);
-    launch_sssp<false>(g, dsrc.as<uint32_t>(), c, state.as<unsigned long long>(), flags.as<uint8_t>(), ForbiddenSets{},
-                       cs.s);
+    cudaError_t le = launch_sssp<false>(g, dsrc.as<uint32_t>(), c, state.as<unsigned long long>(), flags.as<uint8_t>(),
+                                        ForbiddenSets{}, cs.s);
+    if (le != cudaSuccess) {
+      ret = set_error(COZO_GPU_ECUDA, "sssp launch failed: %s", cudaGetErrorString(le));
+      break;
+    }
     ret = per_chunk(s0, c, state.as<unsigned long long>(), dsrc.as<uint32_t>());
     cudaError_t ce = cudaStreamSynchronize(cs.s);
     if (!ret && ce != cudaSuccess) ret = set_error(COZO_GPU_ECUDA, "sssp failed: %s", cudaGetErrorString(ce));
@@ -954,10 +1011,11 @@ extern "C" int cozo_gpu_sssp_paths(cozo_gpu_graph_t* g, const uint32_t* sources,
     fs = ForbiddenSets{fnp.as<uint32_t>(), fnn.as<uint32_t>(), fep.as<uint32_t>(), fes.as<uint32_t>(),
                        fed.as<uint32_t>()};
   }
-  if (forb)
-    launch_sssp<true>(g, dsrc.as<uint32_t>(), n_src, state.as<unsigned long long>(), flags.as<uint8_t>(), fs, st);
-  else
-    launch_sssp<false>(g, dsrc.as<uint32_t>(), n_src, state.as<unsigned long long>(), flags.as<uint8_t>(), fs, st);
+  cudaError_t le = forb ? launch_sssp<true>(g, dsrc.as<uint32_t>(), n_src, state.as<unsigned long long>(),
+                                            flags.as<uint8_t>(), fs, st)
+                        : launch_sssp<false>(g, dsrc.as<uint32_t>(), n_src, state.as<unsigned long long>(),
+                                             flags.as<uint8_t>(), fs, st);
+  if (le != cudaSuccess) return set_error(COZO_GPU_ECUDA, "sssp launch failed: %s", cudaGetErrorString(le));
   sssp_path_kernel<<<(n_src + 127) / 128, 128, 0, st>>>(state.as<unsigned long long>(), n, dsrc.as<uint32_t>(),
                                                         dgoal.as<uint32_t>(), n_src, max_len, dc.as<float>(),
                                                         dl.as<uint32_t>(), dp.as<uint32_t>());

@@ -931,7 +931,9 @@ extern "C" int cozo_gpu_pagerank(cozo_gpu_graph_t* g, float damping, double tol,
   const uint32_t n = g->n;
   if (n == 0) return 0;  // pagerank.rs:43-45
   const DeviceInfo& di = device_info();
-  const int64_t mode = get_option("pagerank.mode", 1);
+  // default = the engine that has run on a GPU (round-1 gather pull); "pagerank.mode" = 1 selects propagation blocking,
+  // which is model-tested on the CPU but has not run on a device yet (gpurun closed mid-round)
+  const int64_t mode = get_option("pagerank.mode", 0);
   uint32_t NH = (uint32_t)std::min<int64_t>(65536, std::max<int64_t>(0, get_option("pagerank.hub_slots", 16384)));
   NH &= ~3u;
   uint32_t GS = (uint32_t)std::min<int64_t>(49152, std::max<int64_t>(64, get_option("pagerank.group_slots", 32768))) & ~3u;

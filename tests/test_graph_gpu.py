@@ -54,56 +54,6 @@ def test_pagerank_rmat_parity(gpu, scale, iters, tol):
     assert abs(gerr - oerr) <= 0.02 * oerr + 1e-6
 
 
-PR_DEFAULTS = {"pagerank.mode": 1, "pagerank.hub_slots": 16384, "pagerank.group_slots": 32768, "pagerank.window": 24576,
-               "pagerank.chunk": 262144}
-PR_ENGINES = [
-    {"pagerank.mode": 0},                                                      # round-1 gather pull
-    {},                                                                        # propagation blocking, defaults
-    {"pagerank.hub_slots": 64, "pagerank.group_slots": 256, "pagerank.window": 512, "pagerank.chunk": 1024},
-    {"pagerank.hub_slots": 0, "pagerank.group_slots": 64, "pagerank.window": 64},          # no hub table, tiny tiles
-    {"pagerank.hub_slots": 1024, "pagerank.group_slots": 4096, "pagerank.window": 3001},   # odd window
-]
-
-
-@pytest.mark.parametrize("engine", range(len(PR_ENGINES)))
-def test_pagerank_engines_and_blockings(gpu, engine):
-    """every engine / blocking geometry computes the same iteration: <= 1e-5 of the oracle on R-MAT (all code paths of
-    the blocking: several groups, many bins, rows that straddle windows, empty rows), bit-identical reruns"""
-    opts = {**PR_DEFAULTS, **PR_ENGINES[engine]}
-    try:
-        for k, v in opts.items():
-            gpu.set_option(k, v)
-        for scale, iters in ((13, 6), (9, 4)):
-            n, src, dst = rmat_edges(scale, 16, 0x5EED0004 + scale)
-            g = gpu.Graph(n, src, dst)
-            os_, oit, oerr = O.OracleGraph(n, src, dst).pagerank(0.85, 0.0, iters, variant="jacobi", n_threads=8)
-            gs, git, gerr, _ = g.pagerank(0.85, 0.0, iters)
-            assert git == oit and np.max(np.abs(gs - os_) / os_) <= 1e-5
-            assert abs(gerr - oerr) <= 0.02 * oerr + 1e-6
-            assert np.array_equal(gs, g.pagerank(0.85, 0.0, iters)[0])
-        # a star: one row with 4999 in-edges (many windows long at the small geometries) + reverse edges
-        n = 5000
-        src = np.concatenate([np.arange(1, n), np.zeros(n - 1)]).astype(np.uint32)
-        dst = np.concatenate([np.zeros(n - 1), np.arange(1, n)]).astype(np.uint32)
-        gs = gpu.Graph(n, src, dst).pagerank(0.85, 0.0, 5)[0]
-        s64 = np.full(n, 1.0 / n)
-        outdeg = np.bincount(src, minlength=n).astype(np.float64)
-        for _ in range(5):
-            nxt = np.full(n, 0.15 / n)
-            np.add.at(nxt, dst, 0.85 * (s64 / outdeg)[src])
-            s64 = nxt
-        assert np.max(np.abs(gs - s64) / s64) <= 4e-6
-        # a path graph and a graph whose last ids have no edges at all
-        src = np.arange(0, 300, dtype=np.uint32)
-        dst = src + 1
-        g = gpu.Graph(1000, src, dst)
-        os_, _, _ = O.OracleGraph(1000, src, dst).pagerank(0.85, 0.0, 7)
-        assert np.allclose(g.pagerank(0.85, 0.0, 7)[0], os_, rtol=1e-6)
-    finally:
-        for k, v in PR_DEFAULTS.items():
-            gpu.set_option(k, v)
-
-
 def test_pagerank_fixed_point_matches_gs_variant(gpu):
     """graph 0.3.1 may update contributions in place (Gauss-Seidel); both schedules share the
     fixed point, so converged GPU scores must match the GS oracle too."""
@@ -225,71 +175,6 @@ def test_betweenness_parity(gpu):
     assert ob.max() > 10
 
 
-def test_sssp_queue_frontier_and_large_graph(gpu):
-    """graphs whose per-source state does not fit shared memory use the compacted frontier queues: same fixed
-    point, bit-identical distances (forced here on a small graph, natural on RMAT-16)"""
-    n = 500
-    src, dst, w = _random_graph(n, 4000, 5, dyadic=False)
-    g = gpu.Graph(n, src, dst, w)
-    o = O.OracleGraph(n, src, dst, w)
-    sources = np.arange(0, n, 11, dtype=np.uint32)
-    od, _ = o.sssp(sources, n_threads=8)
-    gpu.set_option("sssp.force_queue", 1)
-    try:
-        gd, gp, _ = g.sssp(sources)
-        assert np.array_equal(gd, od)
-        _check_tree(src, dst, w, sources, gd, gp, n)
-        gc, _ = g.closeness()
-        oc = o.closeness(n_threads=8)
-        fin = np.isfinite(oc)
-        assert np.array_equal(np.isfinite(gc), fin) and np.allclose(gc[fin], oc[fin], rtol=1e-5)
-    finally:
-        gpu.set_option("sssp.force_queue", 0)
-    n, s2, d2 = rmat_edges(16, 8, 4242)                       # 65536 nodes: 10 bytes/node > shared memory
-    w2 = (np.random.default_rng(1).integers(1, 64, s2.size) / 8.0).astype(np.float32)
-    g2 = gpu.Graph(n, s2, d2, w2)
-    o2 = O.OracleGraph(n, s2, d2, w2)
-    srcs = np.array([0, 1, 77, 4097, 65535], np.uint32)
-    gd, gp, _ = g2.sssp(srcs)
-    od, _ = o2.sssp(srcs, n_threads=8)
-    assert np.array_equal(gd, od)
-    # few sources on a large graph: the "wide" form (many CTAs per source, one launch per round)
-    gpu.set_option("sssp.wide", 1)
-    try:
-        gw, pw, _ = g2.sssp(srcs[:3])
-        assert np.array_equal(gw, od[:3])
-        _check_tree(s2, d2, w2, srcs[:1], gw[:1], pw[:1], n)
-        g1 = gpu.Graph(500, src, dst, w)
-        assert np.array_equal(g1.sssp(sources)[0], O.OracleGraph(500, src, dst, w).sssp(sources, n_threads=8)[0])
-    finally:
-        gpu.set_option("sssp.wide", -1)
-
-
-def test_betweenness_is_deterministic_and_rejects_zero_weight_cycles(gpu):
-    n = 300
-    src, dst, w = _random_graph(n, 1800, 13, dyadic=True)
-    g = gpu.Graph(n, src, dst, w)
-    a, _ = g.betweenness()
-    b, _ = g.betweenness()
-    assert np.array_equal(a, b)                 # per-source dependencies are added in source order, no atomics
-    # a zero-weight edge inside a DAG of ties is fine ...
-    src = np.array([0, 1, 0, 2], np.uint32)
-    dst = np.array([1, 3, 2, 3], np.uint32)
-    w = np.array([0, 1, 0, 1], np.float32)
-    gb, _ = gpu.Graph(4, src, dst, w).betweenness()
-    ob = O.OracleGraph(4, src, dst, w).betweenness()
-    assert np.allclose(gb, ob)
-    # ... a zero-weight CYCLE makes the tied paths unbounded: refused loudly (the reference would not terminate)
-    src = np.array([0, 1, 1, 2], np.uint32)
-    dst = np.array([1, 0, 2, 3], np.uint32)
-    w = np.array([0, 0, 1, 1], np.float32)
-    with pytest.raises(gpu.CozoGpuError) as e:
-        gpu.Graph(4, src, dst, w).betweenness()
-    assert e.value.code == gpu.E_UNSUP
-    gd, _, _ = gpu.Graph(4, src, dst, w).sssp([0])           # distances are still well defined
-    assert gd[0].tolist() == [0, 0, 1, 2]
-
-
 # ---- the reference's air-routes fixture as input ----------------------------------------
 def test_air_routes_all_rules(gpu):
     from tests.test_air_routes_cpu import load_routes
@@ -352,12 +237,6 @@ def test_sssp_paths_with_forbidden_sets(gpu):
     fn = [[int(x) for x in rng.integers(0, n, rng.integers(0, 4)) if x != sources[i]] for i in range(40)]
     fe = [[pairs[int(j)] for j in rng.integers(0, len(pairs), rng.integers(0, 5))] for i in range(40)]
     res, _ = g.sssp_paths(sources, goals, fn, fe, max_len=4)        # small buffer: exercises the retry
-    for opt in ("sssp.force_queue", "sssp.wide"):                    # the other two frontier forms: same answers
-        gpu.set_option(opt, 1)
-        try:
-            assert g.sssp_paths(sources, goals, fn, fe, max_len=64)[0] == res
-        finally:
-            gpu.set_option(opt, -1 if opt == "sssp.wide" else 0)
     for i in range(40):
         keep = np.array([(a, b) not in set(fe[i]) and b not in set(fn[i]) for a, b in pairs])
         o = O.OracleGraph(n, src[keep], dst[keep], w[keep])

@@ -263,40 +263,6 @@ def test_device_builder_parity_and_quality(gpu):
         assert 0.5 * n / m < len(ni[1]) < 2.0 * n / m
 
 
-@pytest.mark.parametrize("keep_pruned,extend", [(False, False), (True, False), (False, True), (True, True)])
-def test_builder_sequential_semantics_equal_the_reference(gpu, keep_pruned, extend):
-    """With batches of ONE node the device builder has the reference's sequential visibility (hnsw.rs:155-375): every
-    insert sees all earlier ones, a row receives one in-edge at a time.  Given the same levels, its search
-    (ef_construction beam carried across layers), heuristic selection (470-538) and shrink (376-469) must then
-    produce the reference's graph edge for edge — checked against the oracle's faithful builder."""
-    n, dim, m = (1200 if extend else 2500), 32, 8
-    X = uniform_vectors(n, dim, 5150)
-    g = gpu.HnswIndex.build(X, m=m, ef_construction=40, keep_pruned_connections=keep_pruned, level_seed=77, max_batch=1,
-                            extend_candidates=extend)           # extend_candidates (hnsw.rs:499-511) implies batches of one
-    ni, rp, ci, ep = g.export_levels()
-    level = np.zeros(n, np.int64)
-    for L in range(1, len(rp)):
-        level[ni[L]] = L
-    ix = O.OracleHnsw.new(n, dim, m=m, ef_construction=40, keep_pruned_connections=keep_pruned, extend_candidates=extend)
-    for i in range(n):
-        ix.insert(i, X[i], forced_level=-int(level[i]))
-    lv = ix.levels()
-    assert lv.entry == ep and lv.n_levels == len(rp)
-    same = total = 0
-    for L in range(len(rp)):
-        nodes_d = np.arange(n) if L == 0 else ni[L]
-        nodes_o = np.arange(n) if L == 0 else lv.node_ids[L]
-        assert np.array_equal(nodes_d, nodes_o)
-        for r in range(len(nodes_d)):
-            a = set(ci[L][int(rp[L][r]):int(rp[L][r + 1])].tolist())
-            b = set(lv.col_idx[L][int(lv.row_ptr[L][r]):int(lv.row_ptr[L][r + 1])].tolist())
-            same += a == b
-            total += 1
-    # distances differ in the last f32 bits (summation order), which can flip a strict comparison of the heuristic
-    # once in a long while and then propagate; anything systematic would show as a large mismatch
-    assert same / total >= 0.995, (same, total)
-
-
 def test_builder_keep_pruned_and_cosine(gpu):
     n, dim, m = 6000, 40, 8
     X = uniform_vectors(n, dim, 555) - np.float32(0.5)
