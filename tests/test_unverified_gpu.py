@@ -132,15 +132,16 @@ def test_betweenness_is_deterministic_and_rejects_zero_weight_cycles(gpu):
     gb, _ = gpu.Graph(4, src, dst, w).betweenness()
     ob = O.OracleGraph(4, src, dst, w).betweenness()
     assert np.allclose(gb, ob)
-    # ... a zero-weight CYCLE makes the tied paths unbounded: refused loudly (the reference would not terminate)
-    src = np.array([0, 1, 1, 2], np.uint32)
-    dst = np.array([1, 0, 2, 3], np.uint32)
-    w = np.array([0, 0, 1, 1], np.float32)
+    # ... a zero-weight CYCLE that does not pass through the source makes the tied paths unbounded: refused loudly
+    # (the reference's enumeration would not terminate).  0 -> 1 (1.0), 1 <-> 2 at weight 0, 2 -> 3 (1.0)
+    src = np.array([0, 1, 2, 2], np.uint32)
+    dst = np.array([1, 2, 1, 3], np.uint32)
+    w = np.array([1, 0, 0, 1], np.float32)
     with pytest.raises(gpu.CozoGpuError) as e:
         gpu.Graph(4, src, dst, w).betweenness()
     assert e.value.code == gpu.E_UNSUP
     gd, _, _ = gpu.Graph(4, src, dst, w).sssp([0])           # distances are still well defined
-    assert gd[0].tolist() == [0, 0, 1, 2]
+    assert gd[0].tolist() == [0, 1, 1, 2]
 
 
 def test_sssp_paths_in_the_queue_and_wide_forms(gpu):
