@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libcozo_gpu.so")
 SOURCES = ["common.cu", "hnsw.cu", "hnsw_f64.cu", "hnsw_build.cu", "graph.cu", "pagerank.cu", "merge.cu", "sharded.cu"]
-HEADERS = ["common.cuh", "hnsw_device.cuh", "hnsw_host.hpp", "graph_host.hpp", "pagerank_pb.cuh", "graph_kernels.cuh", os.path.join("..", "..", "include", "cozo_gpu.h")]
+HEADERS = ["common.cuh", "hnsw_device.cuh", "hnsw_host.hpp", "graph_host.hpp", "pagerank_pb.cuh", "graph_kernels.cuh", "hnsw_build_kernels.cuh", os.path.join("..", "..", "include", "cozo_gpu.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

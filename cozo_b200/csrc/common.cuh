@@ -1,6 +1,22 @@
 // common.cuh — error plumbing, options and small device helpers shared by the
 // kernels of libcozo_gpu.so (sm_100a only).
 #pragma once
+#ifdef COZO_CPU_EMU
+// CPU SIMT emulation (tests/emu/cuda_emu.hpp, test infrastructure): the few helpers device code needs, without CUDA
+#include <stdint.h>
+
+#include "../../include/cozo_gpu.h"
+namespace cozo {
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+inline float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+inline float4 ldg_nc_f4(const float4* p) { return *p; }
+inline void prefetch_l2(const void*) {}
+}  // namespace cozo
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -84,6 +100,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -94,3 +112,4 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
 #endif
 
 }  // namespace cozo
+#endif  // COZO_CPU_EMU

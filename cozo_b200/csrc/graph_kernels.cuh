@@ -2,13 +2,7 @@
 // forms, closeness, betweenness, clustering and the read-out kernels.  A header so that the same source is compiled by
 // nvcc into libcozo_gpu.so and by tests/emu (a CPU SIMT emulator, test infrastructure) into a host program.
 #pragma once
-#ifdef COZO_CPU_EMU
-namespace cozo {
-constexpr uint32_t NONE = 0xFFFFFFFFu;
-}
-#else
 #include "common.cuh"
-#endif
 
 namespace cozo {
 

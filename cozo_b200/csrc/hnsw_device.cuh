@@ -255,7 +255,7 @@ __device__ __forceinline__ void search_level(const HnswDev& g, WarpCtx& w, const
       // the next pop is most likely one of the following entries: pull their adjacency rows into L2
       uint32_t nxt = w.fi[ci + 1 + lane];
       if (!(nxt & EXPANDED))
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(g.adj0 + (size_t)nxt * g.s0));
+        prefetch_l2(g.adj0 + (size_t)nxt * g.s0);
     }
     // hnsw_get_neighbours (hnsw.rs:588-629): one padded row
     const uint32_t* row;
@@ -389,7 +389,7 @@ __device__ __forceinline__ void coop_search_level(const HnswDev& g, WarpCtx& w, 
           w.nodes_expanded++;
           if (level == 0 && ci + 1 + lane < w.len && lane < 2) {
             uint32_t nxt = w.fi[ci + 1 + lane];
-            if (!(nxt & EXPANDED)) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.adj0 + (size_t)nxt * g.s0));
+            if (!(nxt & EXPANDED)) prefetch_l2(g.adj0 + (size_t)nxt * g.s0);
           }
           row = level == 0 ? g.adj0 + (size_t)cand * g.s0
                            : g.adj_up + (size_t)(g.upper_off[cand] + level - 1) * g.su;

@@ -3,17 +3,7 @@
 // nvcc into libcozo_gpu.so and, by tests/emu (a CPU SIMT emulator, test infrastructure), into a host program that runs
 // the passes thread for thread — the engine has not run on a GPU yet.
 #pragma once
-#ifdef COZO_CPU_EMU
-namespace cozo {
-constexpr uint32_t NONE = 0xFFFFFFFFu;
-inline float warp_sum(float v) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-}  // namespace cozo
-#else
 #include "common.cuh"
-#endif
 
 namespace cozo {
 

@@ -51,3 +51,66 @@ def test_graph_device_code(exes, args):
     """SSSP in all frontier forms (with and without forbidden sets), closeness, betweenness (+ ordered reduction, run
     twice), zero-weight-cycle flag, clustering vs host Dijkstra / Brandes / brute force"""
     _run(exes["graph_emu"], *args)
+
+
+def _build_graphs(exe, tmp, n, dim, m, efc, keep, extend, seed):
+    import struct
+
+    import numpy as np
+
+    from oracle import oracle as O
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, dim), dtype=np.float32)
+    level = np.minimum(np.floor(-np.log(rng.random(n)) / np.log(m)), 15).astype(np.uint8)     # the level law, hnsw.rs:46-52
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    open(fin, "wb").write(X.tobytes() + level.tobytes())
+    r = subprocess.run([exe, fin, fout, str(n), str(dim), str(m), str(efc), str(int(keep)), str(int(extend))],
+                       capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0 and "EMU_OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+    buf = open(fout, "rb").read()
+    nl, entry = struct.unpack_from("II", buf, 0)
+    off, dev = 8, []
+    for _ in range(nl):
+        rows, = struct.unpack_from("I", buf, off)
+        off += 4
+        d = {}
+        for _ in range(rows):
+            i, deg = struct.unpack_from("II", buf, off)
+            off += 8
+            d[i] = set(struct.unpack_from(f"{deg}I", buf, off))
+            off += 4 * deg
+        dev.append(d)
+    ix = O.OracleHnsw.new(n, dim, m=m, ef_construction=efc, keep_pruned_connections=keep, extend_candidates=extend)
+    for i in range(n):
+        ix.insert(i, X[i], forced_level=-int(level[i]))
+    lv = ix.levels()
+    assert lv.n_levels == nl and lv.entry == entry
+    same = total = 0
+    for L in range(nl):
+        nodes = np.arange(n) if L == 0 else lv.node_ids[L]
+        assert sorted(dev[L]) == [int(x) for x in nodes]
+        for r_, node in enumerate(nodes):
+            ref = {int(x) for x in lv.col_idx[L][int(lv.row_ptr[L][r_]):int(lv.row_ptr[L][r_ + 1])]}
+            same += ref == dev[L][int(node)]
+            total += 1
+    return same, total
+
+
+_LONG = os.environ.get("COZO_EMU_LONG") == "1"
+
+
+@pytest.mark.parametrize("n,efc,keep,extend", [
+    (64, 12, False, False),
+    (40, 10, True, True),
+    pytest.param(120, 16, False, False, marks=pytest.mark.skipif(not _LONG, reason="minutes under the emulator; COZO_EMU_LONG=1")),
+    pytest.param(100, 16, True, False, marks=pytest.mark.skipif(not _LONG, reason="minutes under the emulator; COZO_EMU_LONG=1")),
+    pytest.param(90, 12, False, True, marks=pytest.mark.skipif(not _LONG, reason="minutes under the emulator; COZO_EMU_LONG=1")),
+    pytest.param(90, 12, True, True, marks=pytest.mark.skipif(not _LONG, reason="minutes under the emulator; COZO_EMU_LONG=1")),
+])
+def test_builder_fidelity_device_code(tmp_path, n, efc, keep, extend):
+    """the index builder's kernels (batch search with the TMA ring, heuristic selection with / without candidate
+    extension, link / shrink) in fidelity mode == the oracle's faithful hnsw_put_vector, edge for edge, given the same
+    levels.  Measured with COZO_EMU_LONG=1: 156/156, 127/127 (keep_pruned), 117/118 (extend), 114/114 (both) rows."""
+    exe = _build("hnsw_build_emu", str(tmp_path))
+    same, total = _build_graphs(exe, str(tmp_path), n, 16, 4, efc, keep, extend, seed=n + efc)
+    assert same >= total - max(1, total // 100), (same, total)    # a strict f32 comparison may flip once in a while
