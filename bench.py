@@ -79,6 +79,9 @@ def parse():
     ap.add_argument("--device-gen", type=int, default=-1, help="1/0: generate the corpus in HBM / on the host (-1: HBM above 2M rows)")
     ap.add_argument("--out", default=None, help="--impl export-graph: where to write the graph")
     ap.add_argument("--scale", type=int, default=24, help="pagerank: RMAT scale")
+    ap.add_argument("--watchdog-s", type=int, default=int(os.environ.get("COZO_BENCH_WATCHDOG_S", 840)),
+                    help="end the process (rc 3) if the run has not finished after this many seconds: a wedged kernel "
+                         "must not hold the GPU box until the caller's limit (0 = off)")
     a = ap.parse_args()
     if a.workload in WORKLOADS:
         rows, batch, k, tile, scaling = WORKLOADS[a.workload]
@@ -412,8 +415,25 @@ def run_pagerank(a):
 
 
 # ---------------------------------------------------------------------------------------------------
+def arm_watchdog(seconds):
+    """A daemon thread that ends the process even when the main thread sits inside a CUDA call."""
+    if seconds <= 0:
+        return
+    import threading
+
+    def fire():
+        sys.stderr.write(f"bench.py: watchdog: not finished after {seconds} s, exiting (rc 3)\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def main():
     a = parse()
+    if a.impl == "ours":
+        arm_watchdog(a.watchdog_s)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

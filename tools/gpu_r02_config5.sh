@@ -6,7 +6,7 @@ N=${N:-8}
 run() { # name, extra args
   name=$1; shift
   timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29671 \
-    bench.py --gpus $N "$@" > gpurun_out/c5/$name.json 2> gpurun_out/c5/$name.err
+    bench.py --gpus $N --watchdog-s 1450 "$@" > gpurun_out/c5/$name.json 2> gpurun_out/c5/$name.err
   echo "== $name rc=$?"; tail -c 3000 gpurun_out/c5/$name.json; tail -3 gpurun_out/c5/$name.err
 }
 free -g | head -2
