@@ -126,7 +126,7 @@ int main(int argc, char** argv) {
   // ---- iterations with the product's passes ------------------------------------------------------------------------
   const float damping = 0.85f, init = 1.0f / (float)n, base = (1.0f - damping) / (float)n;
   const size_t slack = 65536 + 8;
-  std::vector<float> scores(n, init), c0(n + slack, 0.f), c1(n + slack, 0.f), vals(pad + 16, 0.f), msum(n, 0.f);
+  std::vector<float> scores(n, init), c0(n + slack, 0.f), c1(n + slack, 0.f), vals(std::max<uint64_t>(pad, 8) + 8, 0.f), msum(n, 0.f);
   std::vector<float> part_a(std::max(NB, 1u), 0.f), part_z(std::max(NB, 1u), 0.f);
   for (uint32_t r = 0; r < n; ++r) c0[r] = od_slot[r] ? init / (float)od_slot[r] : 0.f;
   alignas(16) unsigned long long err[4];

@@ -13,9 +13,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 
 
+# COZO_EMU_SANITIZE=1: the same harnesses under AddressSanitizer + UBSan (the buffers a kernel touches are host
+# allocations of the size the product's host code gives them, so an out-of-bounds access in device code is reported)
+_SANITIZE = ["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if os.environ.get("COZO_EMU_SANITIZE") == "1" else []
+
+
 def _build(name, tmp):
     exe = os.path.join(tmp, name)
-    r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-o", exe, os.path.join(EMU, name + ".cpp")],
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", *_SANITIZE, "-o", exe, os.path.join(EMU, name + ".cpp")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return exe
@@ -27,8 +32,11 @@ def exes(tmp_path_factory):
     return {n: _build(n, tmp) for n in ("pagerank_pb_emu", "graph_emu")}
 
 
-def _run(exe, *args, timeout=600):
-    r = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=timeout)
+_ENV = dict(os.environ, ASAN_OPTIONS="detect_leaks=0", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+
+
+def _run(exe, *args, timeout=1800):
+    r = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=timeout, env=_ENV)
     assert r.returncode == 0 and "EMU_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
     return r.stdout
 
@@ -65,7 +73,7 @@ def _build_graphs(exe, tmp, n, dim, m, efc, keep, extend, seed):
     fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
     open(fin, "wb").write(X.tobytes() + level.tobytes())
     r = subprocess.run([exe, fin, fout, str(n), str(dim), str(m), str(efc), str(int(keep)), str(int(extend))],
-                       capture_output=True, text=True, timeout=1800)
+                       capture_output=True, text=True, timeout=1800, env=_ENV)
     assert r.returncode == 0 and "EMU_OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
     buf = open(fout, "rb").read()
     nl, entry = struct.unpack_from("II", buf, 0)
