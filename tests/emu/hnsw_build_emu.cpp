@@ -3,7 +3,9 @@
 // the CPU SIMT emulator in FIDELITY mode (batches of one node, as hnsw_insert_range does for max_batch = 1 and for
 // extend_candidates), then writes the graph.  tests/test_emu_cpu.py builds the same index with the oracle's faithful
 // builder (same levels) and compares the two graphs edge for edge.
-// Usage: hnsw_build_emu in.bin out.bin n dim m ef_c keep_pruned extend
+// With max_batch > 1 it runs the DEFAULT (throughput) mode instead: batches of min(max_batch, linked/16) nodes that do
+// not see each other, K1 with 4 warps per CTA, in-edges sorted by (layer, target) and linked one warp per target.
+// Usage: hnsw_build_emu in.bin out.bin n dim m ef_c keep_pruned extend [max_batch = 1]
 //   in.bin  = f32 X[n*dim] then u8 level[n];  out.bin = per level L: u32 n_rows, then per row: u32 id, u32 deg, u32 ids[deg]
 #include "cuda_emu.hpp"
 
@@ -21,6 +23,9 @@ int main(int argc, char** argv) {
   const uint32_t n = (uint32_t)atoi(argv[3]), dim = (uint32_t)atoi(argv[4]), m = (uint32_t)atoi(argv[5]);
   const uint32_t ef_c = (uint32_t)atoi(argv[6]);
   const int keep_pruned = atoi(argv[7]), extend = atoi(argv[8]);
+  uint32_t max_batch = argc > 9 ? (uint32_t)atoi(argv[9]) : 1u;
+  if (extend || max_batch == 0) max_batch = 1;  // as hnsw_insert_range
+  max_batch = std::min(max_batch, n);
   if (dim > 128 || dim % 4) return 2;
   std::vector<float> X((size_t)n * dim);
   std::vector<uint8_t> level(n);
@@ -72,7 +77,7 @@ int main(int argc, char** argv) {
   const uint32_t mcap = std::max(b.m_max0, b.m_max);
   uint32_t max_lvl = 0;
   for (auto l : level) max_lvl = std::max<uint32_t>(max_lvl, l);
-  const uint32_t Tcap = max_lvl + 1;
+  const uint32_t Tcap = max_batch * (max_lvl + 1);
   std::vector<unsigned long long> ext_keys;
   std::vector<float> ext_d;
   std::vector<uint32_t> ext_id;
@@ -92,10 +97,12 @@ int main(int argc, char** argv) {
   // ---- scratch of hnsw_insert_range ---------------------------------------------------------------------------------
   const uint32_t ns = 4;
   const SmemLayout lay = make_layout(ef_c, ns, g.ld);
+  const uint32_t wpc = 4;  // warps per CTA of K1
   const uint32_t nwords = round_up((n + 31) / 32, 4), logcap = std::max<uint32_t>(4096u, 64u * ef_c);
-  std::vector<uint32_t> vis(nwords, 0), vlog(logcap), counters(16, 0);
+  const uint32_t max_grid1 = (max_batch + wpc - 1) / wpc;
+  std::vector<uint32_t> vis((size_t)max_grid1 * wpc * nwords, 0), vlog((size_t)max_grid1 * wpc * logcap), counters(16, 0);
   const uint64_t req_cap = (uint64_t)Tcap * mcap;
-  std::vector<uint32_t> coff(2), lnode(Tcap), llevel(Tcap), cand_id((size_t)Tcap * ef_c), cand_cnt(Tcap), req_src(req_cap), perm(req_cap),
+  std::vector<uint32_t> coff(max_batch + 1), lnode(Tcap), llevel(Tcap), cand_id((size_t)Tcap * ef_c), cand_cnt(Tcap), req_src(req_cap), perm(req_cap),
       perm2(req_cap), heads(req_cap);
   std::vector<float> cand_d((size_t)Tcap * ef_c), req_d(req_cap);
   std::vector<unsigned long long> req_key(req_cap), req_key2(req_cap);
@@ -106,19 +113,25 @@ int main(int argc, char** argv) {
   g.entry = 0;  // first vector: fresh self-loops only (hnsw.rs:360-373)
   g.top_level = level[0];
   inserted = 1;
-  for (; inserted < n; ++inserted) {
-    const uint32_t id = inserted, top = g.top_level;
-    const uint32_t nl = std::min<uint32_t>(level[id], top) + 1;
-    coff[0] = 0;
-    coff[1] = nl;
-    for (uint32_t L = 0; L < nl; ++L) {
-      lnode[L] = id;
-      llevel[L] = L;
+  uint32_t n_live = 1;
+  while (inserted < n) {
+    const uint32_t bs = std::min<uint32_t>(std::min<uint32_t>(max_batch, std::max<uint32_t>(1u, n_live / 16)), n - inserted);
+    const uint32_t top = g.top_level;
+    uint32_t nl = 0;
+    for (uint32_t i = 0; i < bs; ++i) {
+      coff[i] = nl;
+      const uint32_t cnt = std::min<uint32_t>(level[inserted + i], top) + 1;
+      for (uint32_t L = 0; L < cnt; ++L) {
+        lnode[nl] = inserted + i;
+        llevel[nl] = L;
+        ++nl;
+      }
     }
+    coff[bs] = nl;
     std::fill(counters.begin(), counters.end(), 0);
     BatchParams p{};
-    p.begin = id;
-    p.count = 1;
+    p.begin = inserted;
+    p.count = bs;
     p.top = top;
     p.ef_c = ef_c;
     p.coff = coff.data();
@@ -139,7 +152,10 @@ int main(int argc, char** argv) {
     p.logcap = logcap;
     p.ns = ns;
     p.lay = lay;
-    emu::launch(dim3(1), 32, [&] { build_search_body<NV, COZO_GPU_L2>(g, b, p, smem); }, 120, "K1 build_search");
+    if (max_batch == 1)
+      emu::launch(dim3(1), 32, [&] { build_search_body<NV, COZO_GPU_L2>(g, b, p, smem); }, 120, "K1 build_search");
+    else
+      emu::launch(dim3((bs + wpc - 1) / wpc), wpc * 32, [&] { build_search_body<NV, COZO_GPU_L2>(g, b, p, smem); }, 240, "K1 build_search");
     emu::launch(dim3((nl + 3) / 4), 128, [&] { build_select_body<NV, COZO_GPU_L2>(g, b, p, smem); }, 120, "K2 build_select");
     const uint32_t nreq = counters[1];
     if (nreq > req_cap) { std::fprintf(stderr, "in-edge queue overflow\n"); return 1; }
@@ -155,10 +171,15 @@ int main(int argc, char** argv) {
         if (r == 0 || req_key2[r] != req_key2[r - 1]) heads[nheads++] = r;
       emu::launch(dim3((nheads + 3) / 4), 128, [&] { build_link_body<NV, COZO_GPU_L2>(g, b, req_key2.data(), perm2.data(), req_src.data(), req_d.data(), nreq, heads.data(), nheads, smem); }, 120, "K4 build_link");
     }
-    if (level[id] > g.top_level) {
-      g.top_level = level[id];
-      g.entry = id;
+    for (uint32_t i = 0; i < bs; ++i) {
+      const uint32_t id = inserted + i;
+      if (level[id] > g.top_level) {
+        g.top_level = level[id];
+        g.entry = id;
+      }
     }
+    inserted += bs;
+    n_live += bs;
   }
   for (auto v : vis)
     if (v) { std::fprintf(stderr, "visited bitmap not clean after the build\n"); return 1; }
