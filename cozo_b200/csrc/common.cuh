@@ -1,21 +1,16 @@
 // common.cuh — error plumbing, options and small device helpers shared by the
 // kernels of libcozo_gpu.so (sm_100a only).
 #pragma once
-#ifdef COZO_CPU_EMU
-// CPU SIMT emulation (tests/emu/cuda_emu.hpp, test infrastructure): the few helpers device code needs, without CUDA
+// Two test-only build modes exist besides nvcc (tests/emu is test infrastructure; the product is always
+// built by nvcc): COZO_CPU_EMU = a harness compiles device headers only; COZO_CPU_EMU_LIB = the whole library is
+// compiled against a fake CUDA runtime (tests/emu/fake_cuda/cuda_runtime.h, which defines COZO_CPU_EMU itself).
+#if defined(COZO_CPU_EMU) && !defined(COZO_CPU_EMU_LIB)
 #include <stdint.h>
 
 #include "../../include/cozo_gpu.h"
 namespace cozo {
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
-inline float warp_sum(float v) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-inline float4 ldg_nc_f4(const float4* p) { return *p; }
-inline void prefetch_l2(const void*) {}
-}  // namespace cozo
 #else
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -55,8 +50,18 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 
 __host__ __device__ inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
+#endif
+
 // ---- device helpers ----------------------------------------------------------
-#ifdef __CUDACC__
+#if defined(COZO_CPU_EMU)
+// CPU SIMT emulation: mbarrier / bulk copy come from cuda_emu.hpp, the rest are plain loads
+inline float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+inline float4 ldg_nc_f4(const float4* p) { return *p; }
+inline void prefetch_l2(const void*) {}
+#elif defined(__CUDACC__)
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -112,4 +117,3 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
 #endif
 
 }  // namespace cozo
-#endif  // COZO_CPU_EMU

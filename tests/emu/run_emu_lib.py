@@ -1,0 +1,366 @@
+"""Scenarios that drive libcozo_gpu_emu.so (the library's own .cu files compiled for the CPU, tests/emu/build_emu_lib.py)
+through the same ctypes binding and against the same oracle as the `-m gpu` tests, at sizes an emulator can finish.
+Usage: run_emu_lib.py <path to libcozo_gpu_emu.so> <scenario>.  Prints EMU_OK at the end.  TEST INFRASTRUCTURE ONLY.
+
+It runs in its own process because it points cozo_b200.capi at the emulated library before the first load: the product's
+loader has no such switch (no CPU fallback), this script sets the module attribute by hand.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from cozo_b200 import capi  # noqa: E402
+
+capi.LIB_PATH = os.path.abspath(sys.argv[1])
+assert capi._lib is None
+from oracle import oracle as O  # noqa: E402
+from tests.test_graph_gpu import _check_tree, _random_graph  # noqa: E402
+
+T0 = time.time()
+LONG = os.environ.get("COZO_EMU_LONG") == "1"      # the full matrix (minutes); the default subset keeps the CPU suite short
+
+
+def step(msg):
+    print(f"[{time.time() - T0:7.1f}s] {msg}", flush=True)
+
+
+def opts(**kv):
+    class _Ctx:
+        def __enter__(self):
+            for k, v in kv.items():
+                capi.set_option(k.replace("__", "."), v)
+
+        def __exit__(self, *a):
+            for k in kv:
+                capi.set_option(k.replace("__", "."), -1 if k.startswith("hnsw") else 0)
+    return _Ctx()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def scenario_graph():
+    """graph.cu end to end: staging, SSSP in the three frontier forms, closeness, betweenness, clustering, constrained paths"""
+    n = 60
+    src, dst, w = _random_graph(n, 420, 1)
+    g = capi.Graph(n, src, dst, w)
+    o = O.OracleGraph(n, src, dst, w)
+    for a, b in zip(g.export(), o.export()):
+        assert np.array_equal(a, b)
+    step("CSR staging == oracle")
+    for bad in (([0, 5], [1, 2], None), ([0, 1], [1, 2], [1.0, -2.0]), ([0, 1], [1, 2], [1.0, np.inf])):
+        try:
+            capi.Graph(3, bad[0], bad[1], bad[2])
+            raise AssertionError("bad edges accepted")
+        except capi.CozoGpuError:
+            pass
+    sources = np.arange(0, n, 7, dtype=np.uint32)
+    od, _ = o.sssp(sources, n_threads=2)
+    oc = o.closeness(n_threads=2)
+    fin = np.isfinite(oc)
+    for name, kv in (("flag scan (default)", {}), ("compacted frontier", {"sssp__frontier": 1}), ("wide", {"sssp__wide": 1})):
+        with opts(**kv):
+            gd, gp, _ = g.sssp(sources)
+            assert np.array_equal(gd, od), name
+            _check_tree(src, dst, w, sources, gd, gp, n)
+            if name != "wide":           # closeness = n sources: the wide form (one launch per round) is for few sources
+                gc, _ = g.closeness()
+                assert np.array_equal(np.isfinite(gc), fin) and np.allclose(gc[fin], oc[fin], rtol=1e-5), name
+        step(f"sssp + closeness, {name}: distances bit-identical, predecessor trees valid")
+    # unweighted, with unreachable nodes and zero weights
+    s2 = np.array([0, 1, 2, 5, 5], np.uint32)
+    d2 = np.array([1, 2, 0, 6, 5], np.uint32)
+    w2 = np.array([0, 0.5, 0, 2, 0], np.float32)
+    g2, o2 = capi.Graph(8, s2, d2, w2), O.OracleGraph(8, s2, d2, w2)
+    assert np.array_equal(g2.sssp(np.arange(8, dtype=np.uint32))[0], o2.sssp(np.arange(8, dtype=np.uint32))[0])
+    gu, ou = capi.Graph(n, src, dst), O.OracleGraph(n, src, dst, np.ones(src.size, np.float32))   # no weights == all ones
+    assert np.array_equal(gu.sssp(sources)[0], ou.sssp(sources)[0])
+    step("zero weights / unreachable / unweighted")
+    a, _ = g.betweenness()
+    b, _ = g.betweenness()
+    ob = o.betweenness(n_threads=2)
+    assert np.array_equal(a, b) and np.allclose(a, ob, rtol=1e-4, atol=1e-6)
+    step("betweenness == oracle, rerun bit-identical (ordered reduction)")
+    zs, zd, zw = np.array([0, 1, 0, 2], np.uint32), np.array([1, 3, 2, 3], np.uint32), np.array([0, 1, 0, 1], np.float32)
+    assert np.allclose(capi.Graph(4, zs, zd, zw).betweenness()[0], O.OracleGraph(4, zs, zd, zw).betweenness())
+    cs, cd, cw = np.array([0, 1, 2, 2], np.uint32), np.array([1, 2, 1, 3], np.uint32), np.array([1, 0, 0, 1], np.float32)
+    try:
+        capi.Graph(4, cs, cd, cw).betweenness()
+        raise AssertionError("zero-weight cycle accepted")
+    except capi.CozoGpuError as e:
+        assert e.code == capi.E_UNSUP
+    assert capi.Graph(4, cs, cd, cw).sssp([0])[0][0].tolist() == [0, 1, 1, 2]
+    step("zero-weight tie DAG accepted, zero-weight cycle refused (EUNSUP)")
+    ms, md = np.concatenate([src, dst]), np.concatenate([dst, src])
+    gc_, gt, gdg, _ = capi.Graph(n, ms, md).clustering()
+    oc_, ot, odg = O.OracleGraph(n, ms, md).clustering(n_threads=2)
+    assert np.array_equal(gt, ot) and np.array_equal(gdg, odg) and np.array_equal(gc_, oc_) and ot.max() > 0
+    step("clustering bit-identical")
+    rng = np.random.default_rng(8)
+    pairs = sorted({(int(a), int(b)) for a, b in zip(rng.integers(0, n, 500), rng.integers(0, n, 500)) if a != b})
+    ps = np.array([p[0] for p in pairs], np.uint32)
+    pd = np.array([p[1] for p in pairs], np.uint32)
+    pw = (rng.random(ps.size) * 10 + 0.5).astype(np.float32)
+    gp_ = capi.Graph(n, ps, pd, pw)
+    S = 12
+    srcs, goals = rng.integers(0, n, S).astype(np.uint32), rng.integers(0, n, S).astype(np.uint32)
+    fn = [[int(x) for x in rng.integers(0, n, rng.integers(0, 4)) if x != srcs[i]] for i in range(S)]
+    fe = [[pairs[int(j)] for j in rng.integers(0, len(pairs), rng.integers(0, 5))] for i in range(S)]
+    res, _ = gp_.sssp_paths(srcs, goals, fn, fe, max_len=4)
+    for i in range(S):
+        keep = np.array([(a, b) not in set(fe[i]) and b not in set(fn[i]) for a, b in pairs])
+        oo = O.OracleGraph(n, ps[keep], pd[keep], pw[keep])
+        dd, bb = oo.sssp([int(srcs[i])])
+        cost, path = res[i]
+        exp = float(dd[0, goals[i]])
+        if np.isinf(exp):
+            assert np.isinf(cost) and path == []
+            continue
+        assert cost == exp
+        p, cur = [], int(goals[i])
+        while cur != int(srcs[i]):
+            p.append(cur)
+            cur = int(bb[0, cur])
+        p.append(int(srcs[i]))
+        assert path == p[::-1]
+    for kv in ({"sssp__frontier": 1}, {"sssp__wide": 1}):
+        with opts(**kv):
+            assert gp_.sssp_paths(srcs, goals, fn, fe, max_len=16)[0] == res
+    step("constrained paths (forbidden nodes / edges) == oracle on the pruned graph, in all three frontier forms")
+    # poison set before the call
+    flag = np.ones(1, np.int32)
+    try:
+        g.closeness(poison=flag)
+        raise AssertionError("poisoned call ran")
+    except capi.CozoGpuError as e:
+        assert e.code == capi.E_KILLED
+    step("poison -> EKILLED")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+PR_GEOMETRIES = [
+    {"pagerank__mode": 0},
+    {"pagerank__mode": 1, "pagerank__hub_slots": 16384, "pagerank__group_slots": 32768, "pagerank__window": 24576, "pagerank__chunk": 262144},
+    {"pagerank__mode": 1, "pagerank__hub_slots": 64, "pagerank__group_slots": 256, "pagerank__window": 512, "pagerank__chunk": 1024},
+    {"pagerank__mode": 1, "pagerank__hub_slots": 0, "pagerank__group_slots": 64, "pagerank__window": 64, "pagerank__chunk": 1024},
+    {"pagerank__mode": 1, "pagerank__hub_slots": 8, "pagerank__group_slots": 128, "pagerank__window": 301, "pagerank__chunk": 1024},
+]
+
+
+def scenario_pagerank():
+    """pagerank.cu end to end: slot staging, both engines, blocking (re)staging when the geometry options change"""
+    from tests.util import rmat_edges
+    n, src, dst = rmat_edges(9, 12, 0x5EED0004 + 9)
+    o = O.OracleGraph(n, src, dst)
+    os_, oit, oerr = o.pagerank(0.85, 0.0, 4, variant="jacobi", n_threads=2)
+    ot, otit, _ = o.pagerank(0.85, 1e-3, 30, variant="jacobi", n_threads=2)
+    star_n = 700
+    ss = np.concatenate([np.arange(1, star_n), np.zeros(star_n - 1)]).astype(np.uint32)
+    sd = np.concatenate([np.zeros(star_n - 1), np.arange(1, star_n)]).astype(np.uint32)
+    s64 = np.full(star_n, 1.0 / star_n)
+    outdeg = np.bincount(ss, minlength=star_n).astype(np.float64)
+    for _ in range(4):
+        nxt = np.full(star_n, 0.15 / star_n)
+        np.add.at(nxt, sd, 0.85 * (s64 / outdeg)[ss])
+        s64 = nxt
+    ps = np.arange(0, 90, dtype=np.uint32)
+    o_path, _, _ = O.OracleGraph(300, ps, ps + 1).pagerank(0.85, 0.0, 5)
+    g = capi.Graph(n, src, dst)                     # ONE staged graph: the blocking is rebuilt when the options change
+    gstar = capi.Graph(star_n, ss, sd)
+    gpath = capi.Graph(300, ps, ps + 1)
+    for geo in (PR_GEOMETRIES if LONG else PR_GEOMETRIES[:3]):
+        with opts(**geo):
+            gs, git, gerr, _ = g.pagerank(0.85, 0.0, 4)
+            rel = float(np.max(np.abs(gs - os_) / os_))
+            assert git == oit and rel <= 1e-5, (geo, rel)
+            assert abs(gerr - oerr) <= 0.02 * oerr + 1e-6
+            assert np.array_equal(gs, g.pagerank(0.85, 0.0, 4)[0])          # bit-identical rerun
+            gt, gtit, _, _ = g.pagerank(0.85, 1e-3, 30)
+            assert gtit == otit and np.max(np.abs(gt - ot) / ot) <= 1e-5    # same stopping iteration
+            gst = gstar.pagerank(0.85, 0.0, 4)[0]
+            assert np.max(np.abs(gst - s64) / s64) <= 4e-6                  # a row many windows long
+            assert np.allclose(gpath.pagerank(0.85, 0.0, 5)[0], o_path, rtol=1e-6)   # ids without edges
+        step(f"{geo}: rmat-9 max rel err {rel:.2e}, tol stop at {gtit}, star + path graphs ok, launches "
+             f"{capi.get_option('pagerank.last_launches')}")
+    g0 = capi.Graph(0, np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+    s, it, _, _ = g0.pagerank()
+    assert s.size == 0 and it == 0
+    for geo in (PR_GEOMETRIES[0], PR_GEOMETRIES[2]):
+        with opts(**geo):
+            e0 = capi.Graph(5, np.zeros(0, np.uint32), np.zeros(0, np.uint32)).pagerank(0.85, 0.0, 2)[0]   # no edges
+            assert np.allclose(e0, 0.15 / 5)
+            s3, d3 = np.array([0, 1], np.uint32), np.array([1, 2], np.uint32)
+            assert np.allclose(capi.Graph(3, s3, d3).pagerank(0.85, 0.0, 3)[0], O.OracleGraph(3, s3, d3).pagerank(0.85, 0.0, 3)[0], rtol=1e-6)
+    step("empty graph, no edges, dangling node")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _graph_sets(levels):
+    ni, rp, ci, ep = levels
+    out = []
+    for L in range(len(rp)):
+        nodes = np.arange(len(rp[0]) - 1) if L == 0 else ni[L]
+        out.append({int(v): set(ci[L][int(rp[L][r]):int(rp[L][r + 1])].tolist()) for r, v in enumerate(nodes)})
+    return out, ep
+
+
+def scenario_hnsw():
+    """hnsw_build.cu + hnsw.cu + hnsw_f64.cu + merge.cu end to end through the ctypes binding"""
+    rng = np.random.default_rng(1)
+    n, dim = (140 if LONG else 100), 32
+    X = rng.random((n, dim), dtype=np.float32)
+    Q = rng.random((9, dim), dtype=np.float32)
+    for metric in ((capi.L2, capi.COSINE) if LONG else (capi.L2,)):
+        g = capi.HnswIndex.build(X - (0.5 if metric else 0), metric=metric, m=6, ef_construction=24, keep_pruned_connections=bool(metric))
+        Xm = X - (0.5 if metric else 0)
+        ni, rp, ci, ep = g.export_levels()
+        ix = O.OracleHnsw.from_levels(Xm, O.HnswLevels(ni, rp, ci, ep), metric=metric)
+        oi, od, oc, ost = ix.search(Q - (0.5 if metric else 0), 5, 20, n_threads=2)
+        for mode in (1, 0, 2):
+            with opts(hnsw__mode=mode):
+                gi, gd, gc, st = g.search(Q - (0.5 if metric else 0), 5, 20)
+            assert np.array_equal(gi, oi) and np.allclose(gd, od, rtol=1e-5, atol=1e-6) and np.array_equal(gc, oc)
+            assert st.dist_evals == int(ost[:, 0].sum()) and st.nodes_expanded == int(ost[:, 1].sum())
+        step(f"metric {metric}: build ({n} x {dim}), search modes TMA ring / ld.global.nc / cooperative: ids, distances, "
+             f"traversal counters == oracle")
+        if metric:
+            continue
+        # radius, k > ef, filter mask (trim after the filter), in all modes
+        full_i, full_d, full_c, _ = ix.search(Q, 20, 20, n_threads=2)
+        r = float(np.median(od[:, 3])) * (1 + 1e-4)     # not ON a candidate distance: device and oracle differ in the last ulp
+        assert np.min(np.abs(full_d / r - 1)) > 1e-5
+        keep = rng.random(n) < 0.4
+        for mode in (1, 0, 2):
+            with opts(hnsw__mode=mode):
+                ri, rd, rc, _ = g.search(Q, 5, 20, radius=r)
+                fi, fd, fc, _ = g.search(Q, 5, 20, radius=r, row_pass=keep)
+                ki, kd, kc, _ = g.search(Q, 30, 20)
+            for q in range(len(Q)):
+                cand = [(int(i), float(d)) for i, d in zip(full_i[q, :full_c[q]], full_d[q, :full_c[q]])]
+                assert list(ri[q, :rc[q]]) == [i for i, d in cand if d <= r][:5]
+                assert list(fi[q, :fc[q]]) == [i for i, d in cand if d <= r and keep[i]][:5]
+                assert kc[q] == full_c[q] and list(ki[q, :kc[q]]) == [i for i, _ in cand]
+        step("radius, k > ef, filter mask applied before the trim (all modes)")
+        # stage the exported graph again (the Rust glue's path) and an F64 copy
+        g2 = capi.HnswIndex.stage(X, ni, rp, ci, ep, m_max0=12, m_max=6)
+        assert np.array_equal(g2.search(Q, 5, 20)[0], oi)
+        X64 = rng.random((n, dim)) - 0.5
+        Q64 = rng.random((9, dim)) - 0.5
+        for m64 in (capi.L2, capi.COSINE, capi.IP):
+            g64 = capi.HnswIndex.stage(X64, ni, rp, ci, ep, metric=m64, m_max0=12, m_max=6)
+            ix64 = O.OracleHnsw.from_levels(X64.astype(np.float32), O.HnswLevels(ni, rp, ci, ep), metric=m64)
+            o64i, o64d, o64c, _ = ix64.search_f64(X64, Q64, 5, 20, n_threads=2)
+            g64i, g64d, g64c, _ = g64.search_f64(Q64, 5, 20, row_pass=None)
+            assert np.array_equal(g64i, o64i) and np.allclose(g64d, o64d, rtol=1e-12, atol=1e-14) and np.array_equal(g64c, o64c)
+            f64i, _, f64c, _ = g64.search_f64(Q64, 5, 20, row_pass=keep)
+            fo_i, _, fo_c, _ = ix64.search_f64(X64, Q64, 20, 20, n_threads=2)
+            for q in range(len(Q64)):
+                assert list(f64i[q, :f64c[q]]) == [int(i) for i in fo_i[q, :fo_c[q]] if keep[i]][:5]
+            try:
+                g64.search(Q, 5, 20)
+                raise AssertionError("f32 search on an F64 handle")
+            except capi.CozoGpuError as e:
+                assert e.code == capi.E_INVAL
+        step("re-staged graph; F64 index L2 / Cosine / IP == oracle f64 path, filtered form too")
+        # device-pointer forms: search_dev into caller buffers, top-k merge of two "shards"
+        B, k = len(Q), 5
+        ids = np.zeros((2, B, k), np.uint32)
+        dist = np.zeros((2, B, k), np.float32)
+        cnt = np.zeros(B, np.uint32)
+        Qc = np.ascontiguousarray(Q)
+        g.search_dev(Qc.ctypes.data, B, k, 20, ids[0].ctypes.data, dist[0].ctypes.data, cnt.ctypes.data)
+        g2.search_dev(Qc.ctypes.data, B, k, 20, ids[1].ctypes.data, dist[1].ctypes.data, None)
+        assert np.array_equal(ids[0], oi) and np.array_equal(ids[1], oi)
+        offs = np.array([0, 1000], np.uint64)
+        mi, md = np.zeros((B, k), np.uint64), np.zeros((B, k), np.float32)
+        capi.topk_merge_dev(dist.ctypes.data, ids.ctypes.data, 2, B, k, offs.ctypes.data, mi.ctypes.data, md.ctypes.data)
+        for q in range(B):
+            allp = sorted([(float(dist[s, q, j]), s, int(ids[s, q, j]) + int(offs[s])) for s in range(2) for j in range(k)])
+            assert [p[2] for p in allp[:k]] == mi[q].tolist()
+        step("search_dev + topk_merge_dev")
+
+
+def scenario_hnsw_maintenance():
+    """insert / update / remove / exports on built and staged handles, insert into an empty staged handle"""
+    rng = np.random.default_rng(3)
+    n, dim = 90, 16
+    X = rng.random((n + 30, dim), dtype=np.float32)
+    Q = rng.random((8, dim), dtype=np.float32)
+    g = capi.HnswIndex.build(X[:n], m=5, ef_construction=20)
+    first = g.insert(X[n:n + 20])
+    assert first == n
+    g.update(np.array([3, 4, 50, n + 19], np.uint32), X[n + 20:n + 24])
+    g.remove(np.arange(10, 25, dtype=np.uint32))
+    live = g.export_live()
+    assert live.sum() == n + 20 - 15
+    Xc = X[:n + 20].copy()
+    Xc[[3, 4, 50, n + 19]] = X[n + 20:n + 24]
+    ni, rp, ci, ep = g.export_levels()
+    sets, _ = _graph_sets((ni, rp, ci, ep))
+    for L, rows in enumerate(sets):
+        for v, nb in rows.items():
+            assert not (nb & set(range(10, 25))), "edge to a removed node"
+            assert len(nb) <= (10 if L == 0 else 5)
+    ix = O.OracleHnsw.from_levels(Xc, O.HnswLevels(ni, rp, ci, ep))
+    gi, gd, gc, _ = g.search(Q, 5, 20)
+    oi, od, oc, _ = ix.search(Q, 5, 20, n_threads=2)
+    assert np.array_equal(gi, oi) and np.allclose(gd, od, rtol=1e-5)
+    bi, _ = O.bruteforce_knn(np.where(live[:, None] > 0, Xc, 1e3), Q, 5, n_threads=2)
+    rec = np.mean([len(set(a) & set(b)) / 5 for a, b in zip(gi, bi)])
+    assert rec >= 0.9, rec
+    step(f"insert / update / remove: graph consistent, search == oracle on the exported graph, recall vs brute force {rec:.2f}")
+    dists = g.export_dists()
+    for L in range(len(ci)):
+        nodes = np.arange(len(rp[0]) - 1) if L == 0 else ni[L]
+        for r, v in enumerate(nodes):
+            for e in range(int(rp[L][r]), int(rp[L][r + 1])):
+                d = float(np.sum((Xc[v] - Xc[ci[L][e]]) ** 2, dtype=np.float64))
+                assert abs(dists[L][e] - d) <= 1e-5 * max(d, 1e-6)
+    step("stored edge distances == recomputed")
+    # a handle staged from another handle's export grows by insert (build state derived on demand)
+    gs = capi.HnswIndex.stage(Xc, ni, rp, ci, ep, m_max0=10, m_max=5)
+    f2 = gs.insert(X[n + 24:n + 30], ef_construction=20)
+    assert f2 == n + 20 and (gs.search(Q, 5, 20)[2] == 5).all()
+    # the canary-only index: staged with zero rows, then filled
+    e = capi.HnswIndex.stage(np.zeros((0, dim), np.float32), [np.zeros(0, np.uint32)], [np.zeros(1, np.uint32)], [np.zeros(0, np.uint32)],
+                             0xFFFFFFFF, m_max0=10, m_max=5)
+    assert e.insert(X[:40], ef_construction=20) == 0
+    ei, _, ec, _ = e.search(X[:6], 1, 20)
+    assert (ec == 1).all() and ei[:, 0].tolist() == list(range(6))
+    step("insert into a staged handle and into an empty staged handle")
+
+
+def scenario_builder_fidelity():
+    """hnsw_insert_range in fidelity mode (max_batch = 1) and with extend_candidates == the oracle's sequential builder"""
+    dim, m, efc = 16, 4, 12
+    cases = ((70, False, False), (60, True, False), (48, False, True), (44, True, True))
+    for n, keep, extend in (cases if LONG else (cases[0], cases[2])):
+        X = np.random.default_rng(n).random((n, dim), dtype=np.float32)
+        g = capi.HnswIndex.build(X, m=m, ef_construction=efc, keep_pruned_connections=keep, level_seed=77, max_batch=1, extend_candidates=extend)
+        ni, rp, ci, ep = g.export_levels()
+        level = np.zeros(n, np.int64)
+        for L in range(1, len(rp)):
+            level[ni[L]] = L
+        ix = O.OracleHnsw.new(n, dim, m=m, ef_construction=efc, keep_pruned_connections=keep, extend_candidates=extend)
+        for i in range(n):
+            ix.insert(i, X[i], forced_level=-int(level[i]))
+        lv = ix.levels()
+        assert lv.entry == ep and lv.n_levels == len(rp)
+        dsets, _ = _graph_sets((ni, rp, ci, ep))
+        osets, _ = _graph_sets((lv.node_ids, lv.row_ptr, lv.col_idx, lv.entry))
+        same = sum(dsets[L][v] == osets[L][v] for L in range(len(dsets)) for v in dsets[L])
+        total = sum(len(d) for d in dsets)
+        assert all(sorted(a) == sorted(b) for a, b in zip(dsets, osets))
+        assert same >= total - max(1, total // 100), (same, total)
+        step(f"n={n} keep_pruned={keep} extend_candidates={extend}: {same} / {total} rows identical to the oracle builder's")
+
+
+SCENARIOS = {"graph": scenario_graph, "pagerank": scenario_pagerank, "hnsw": scenario_hnsw,
+             "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity}
+
+if __name__ == "__main__":
+    capi.init(0)
+    SCENARIOS[sys.argv[2]]()
+    print("EMU_OK")

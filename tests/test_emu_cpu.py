@@ -121,8 +121,9 @@ _LONG = os.environ.get("COZO_EMU_LONG") == "1"
 
 
 @pytest.mark.parametrize("n,efc,keep,extend", [
-    (64, 12, False, False),
-    (40, 10, True, True),
+    (40, 10, False, False),
+    pytest.param(40, 10, True, True, marks=pytest.mark.skipif(not _LONG, reason="minutes under the emulator; COZO_EMU_LONG=1 "
+                                                                               "(tests/test_emu_lib_cpu.py covers the same through the C ABI)")),
     pytest.param(120, 16, False, False, marks=pytest.mark.skipif(not _LONG, reason="minutes under the emulator; COZO_EMU_LONG=1")),
     pytest.param(100, 16, True, False, marks=pytest.mark.skipif(not _LONG, reason="minutes under the emulator; COZO_EMU_LONG=1")),
     pytest.param(90, 12, False, True, marks=pytest.mark.skipif(not _LONG, reason="minutes under the emulator; COZO_EMU_LONG=1")),
