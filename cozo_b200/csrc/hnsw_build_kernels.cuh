@@ -337,14 +337,24 @@ __device__ __forceinline__ void build_select_body(const HnswDev& g, const BuildD
   uint32_t ns = heuristic_select<NV, METRIC>(g, cd, cid, ccnt, mm, b.keep_pruned != 0, sel_id, sel_d, lane);
   __syncwarp();
   uint32_t rbase = 0;
+  // The reference writes a neighbour's out edge, its in edge and the shrink of that neighbour one neighbour at a time
+  // (hnsw.rs:279-357).  With extend_candidates a shrink reads the rows of the target's neighbours — the new node among
+  // them — so it sees only the out edges written SO FAR.  In that mode the row starts empty here and the sequential link
+  // step appends out edge r right before it links in edge r.  Without extension nothing reads the new node's row while
+  // its neighbours are linked, and the whole row is written at once.
+  const bool incremental = b.extend != 0;
   if (lane == 0) {
-    *deg = ns;
+    *deg = incremental ? 0u : ns;
     rbase = atomicAdd(p.req_count, ns);
   }
   rbase = __shfl_sync(0xffffffffu, rbase, 0);
+  if (incremental)
+    for (uint32_t j = lane; j < stride; j += 32) ids[j] = NONE;
   for (uint32_t j = lane; j < ns; j += 32) {
-    ids[j] = sel_id[j];  // out edge (hnsw.rs:281-298)
-    ds[j] = sel_d[j];
+    if (!incremental) {
+      ids[j] = sel_id[j];  // out edge (hnsw.rs:281-298)
+      ds[j] = sel_d[j];
+    }
     p.req_key[rbase + j] = ((unsigned long long)level << 32) | sel_id[j];  // in edge (hnsw.rs:300-318)
     p.req_src[rbase + j] = node;
     p.req_d[rbase + j] = sel_d[j];
@@ -386,7 +396,22 @@ __device__ __forceinline__ void build_link_body(const HnswDev& g, const BuildDev
   uint32_t *ids, *degp;
   float* ds;
   uint32_t stride, mm;
-  adj_row(g, b, node, level, ids, ds, degp, stride, mm);
+  if (b.extend) {  // sequential mode, one request per launch: the source's out edge first (hnsw.rs:281-298) ...
+    end = start + 1;
+    const uint32_t r = perm[start];
+    const uint32_t src = req_src[r];
+    uint32_t *sids, *sdeg, sstride, smm;
+    float* sds;
+    adj_row(g, b, src, level, sids, sds, sdeg, sstride, smm);
+    if (lane == 0) {
+      const uint32_t d = *sdeg;
+      sids[d] = node;
+      sds[d] = req_d[r];
+      *sdeg = d + 1;
+    }
+    __syncwarp();
+  }
+  adj_row(g, b, node, level, ids, ds, degp, stride, mm);  // ... then the in edge (hnsw.rs:300-318)
   uint32_t deg = *degp;
   for (uint32_t a0 = start; a0 < end; a0 += 32) {
     const uint32_t na = min(32u, end - a0);

@@ -1,4 +1,5 @@
 """Device code under a CPU SIMT emulator (tests/emu/cuda_emu.hpp; test infrastructure, like oracle/).
+(tests/test_emu_lib_cpu.py goes one step further and runs the whole library, host code included, the same way.)
 
 The kernels that have not run on a GPU yet are compiled from the product's own headers
 (cozo_b200/csrc/pagerank_pb.cuh, graph_kernels.cuh) into host programs: one OS thread per CUDA thread, real barriers,
@@ -117,7 +118,7 @@ def _build_graphs(exe, tmp, n, dim, m, efc, keep, extend, seed):
     return same, total
 
 
-_LONG = os.environ.get("COZO_EMU_LONG") == "1"
+_LONG = True      # every case: seconds since the emulator schedules lanes as fibers (was minutes with a thread per lane)
 
 
 @pytest.mark.parametrize("n,efc,keep,extend", [

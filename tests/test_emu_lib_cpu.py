@@ -6,7 +6,11 @@ Why: gpurun closed mid-round with several code paths never run o
 entry points, their host logic (staging, CUB sorts, launch geometry, chunking, option handling) and the kernels — with
 32-wide warps and real concurrency.  It is a logic check: no performance, no hardware memory model, no NCCL / IPC
 (sharded.cu is stubbed out).  The product never loads this library (tests/emu/run_emu_lib.py points the binding at it by
-hand, in a process of its own).  COZO_EMU_LONG=1 runs the full matrix, COZO_EMU_SANITIZE=1 builds with ASan + UBSan."""
+hand, in a process of its own).  COZO_EMU_SANITIZE=1 builds with ASan + UBSan.
+
+The `-m gpu` test files themselves run against it too (tests/conftest.py honours COZO_EMU_LIB): the host-layer file and
+the quick graph tests in every CPU run, all of test_graph_gpu / test_hnsw_gpu / test_host_gpu / test_unverified_gpu with
+COZO_EMU_LONG=1 (about 40 minutes; recorded in profiles/r02_emu_gpu_testfiles.txt)."""
 import os
 import subprocess
 import sys
@@ -57,3 +61,28 @@ def test_library_scenario(emu_lib, scenario):
     sequential builder edge for edge."""
     out = _run(emu_lib, scenario)
     print(out)
+
+
+def _pytest_on_emu(lib, args, timeout):
+    env = dict(os.environ, COZO_EMU_LIB=lib, COZO_RUN_UNVERIFIED="1", ASAN_OPTIONS="detect_leaks=0")
+    if SANITIZE:
+        env["LD_PRELOAD"] = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", *args], capture_output=True, text=True,
+                       timeout=timeout, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_gpu_test_files_on_the_emulated_library(emu_lib):
+    """the host-layer GPU tests (FixedRule / HnswSearchRA mirrors over the C ABI: PageRank, Dijkstra incl. keep_ties, Yen,
+    centralities, clustering, index build / write-back / put / rm, device filter) and the quick graph tests, unchanged,
+    with the binding pointed at libcozo_gpu_emu.so"""
+    out = _pytest_on_emu(emu_lib, ["-m", "gpu", "tests/test_host_gpu.py", "tests/test_graph_gpu.py", "-k", "not air_routes and not 17-5"], 2400)
+    assert " passed" in out and "failed" not in out
+
+
+@pytest.mark.skipif(os.environ.get("COZO_EMU_LONG") != "1", reason="about 40 minutes; COZO_EMU_LONG=1")
+def test_all_gpu_test_files_on_the_emulated_library(emu_lib):
+    """every -m gpu / gpu_unverified test that does not need torch CUDA tensors, several GPUs or a million vectors"""
+    _pytest_on_emu(emu_lib, ["-m", "gpu or gpu_unverified", "-p", "no:timeout", "tests/test_graph_gpu.py", "tests/test_hnsw_gpu.py",
+                             "tests/test_host_gpu.py", "tests/test_unverified_gpu.py", "-k", "not search_dev_and_merge"], 4 * 3600)
