@@ -32,8 +32,9 @@ def emu_lib(tmp_path_factory):
     return build_emu_lib.build(str(tmp_path_factory.mktemp("emu_lib")), sanitize=SANITIZE)
 
 
-def _run(lib, scenario):
-    env = dict(os.environ, UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1", ASAN_OPTIONS="detect_leaks=0")
+def _run(lib, scenario, sm_count=4):
+    env = dict(os.environ, UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1", ASAN_OPTIONS="detect_leaks=0",
+               COZO_EMU_SM_COUNT=str(sm_count))       # the fake device's SM count: grids of persistent kernels follow it
     if SANITIZE:
         env["LD_PRELOAD"] = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     r = subprocess.run([sys.executable, os.path.join(EMU, "run_emu_lib.py"), lib, scenario], capture_output=True, text=True,
@@ -51,15 +52,16 @@ def test_library_exports_every_abi_symbol(emu_lib):
     assert all(hasattr(L, s) for s in capi.EXPORTS)
 
 
+@pytest.mark.parametrize("sm_count", [4, 148])
 @pytest.mark.parametrize("scenario", ["graph", "pagerank", "hnsw", "hnsw_maintenance", "builder_fidelity"])
-def test_library_scenario(emu_lib, scenario):
+def test_library_scenario(emu_lib, scenario, sm_count):
     """graph: CSR staging, SSSP in three frontier forms, closeness, betweenness (+ zero-weight-cycle refusal), clustering,
     constrained paths, poison.  pagerank: both engines, blocking geometries, restaging on option change, edge cases.
     hnsw: build, three search modes (ids / distances / traversal counters == oracle), radius, k > ef, filter mask, re-staging,
     F64 indexes, device-pointer search + top-k merge.  hnsw_maintenance: insert / update / remove / exports, insert into a
     staged and into an empty staged handle.  builder_fidelity: max_batch = 1 and extend_candidates reproduce the oracle's
     sequential builder edge for edge."""
-    out = _run(emu_lib, scenario)
+    out = _run(emu_lib, scenario, sm_count)
     print(out)
 
 
