@@ -6,7 +6,9 @@ The .cu sources are rewritten on the fly into a scratch directory (the files und
   kernel<<<grid, block, smem, stream>>>(args)   ->  emu::launch_k(grid, block, smem, "kernel", kernel, args)
   extern __shared__ ... name[];                 ->  uint8_t* name = emu::t_dyn_smem;
   the four L2-hint PTX helpers of pagerank.cu   ->  plain loads
-sharded.cu (NCCL + CUDA IPC) is left out; its entry points are stubs that answer COZO_GPU_EUNSUP.
+sharded.cu is built too: NCCL comes from tests/emu/fake_nccl.cpp (libfake_nccl.so next to the library; point
+COZO_GPU_NCCL_LIB at it), where the ranks of a communicator are threads of one process, and CUDA IPC handles are plain
+pointers — so the fused peer-store exchange and its flag barrier run for real between rank threads.
 """
 from __future__ import annotations
 
@@ -18,7 +20,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CSRC = os.path.join(ROOT, "cozo_b200", "csrc")
 EMU = os.path.join(ROOT, "tests", "emu")
-SOURCES = ["common.cu", "hnsw.cu", "hnsw_f64.cu", "hnsw_build.cu", "graph.cu", "pagerank.cu", "merge.cu"]
+SOURCES = ["common.cu", "hnsw.cu", "hnsw_f64.cu", "hnsw_build.cu", "graph.cu", "pagerank.cu", "merge.cu", "sharded.cu"]
 
 ASM_REWRITES = [  # pagerank.cu: L2 eviction-policy hints have no meaning on the CPU
     (re.compile(r'asm volatile\("createpolicy[^;]*;\s*"\s*:\s*"=l"\(p\)\);'), "p = 0;"),
@@ -26,6 +28,11 @@ ASM_REWRITES = [  # pagerank.cu: L2 eviction-policy hints have no meaning on the
      "v = *a; (void)pol;"),
     (re.compile(r'asm volatile\("ld\.global\.nc\.L1::no_allocate\.L2::cache_hint\.u32[^;]*;\s*"\s*:\s*"=r"\(v\)\s*:\s*"l"\(a\),\s*"l"\(pol\)\);'),
      "v = *a; (void)pol;"),
+    # sharded.cu: the flag words of the exchange barrier
+    (re.compile(r'asm volatile\("st\.release\.sys\.global\.u32 \[%0\], %1;" ::"l"\(([^)]*)\), "r"\(([^)]*)\) : "memory"\);'),
+     r"__atomic_store_n(\1, \2, __ATOMIC_RELEASE);"),
+    (re.compile(r'asm volatile\("ld\.acquire\.sys\.global\.u32 %0, \[%1\];" : "=r"\((\w+)\) : "l"\(([^)]*)\) : "memory"\);'),
+     r"\1 = __atomic_load_n(\2, __ATOMIC_ACQUIRE);"),
 ]
 EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?uint8_t\s+(\w+)\[\];")
 
@@ -128,17 +135,15 @@ def build(out_dir: str, sanitize: bool = False) -> str:
         objs.append(obj)
         procs.append((name, subprocess.Popen(["g++", *flags, "-c", cpp, "-o", obj], stdout=subprocess.PIPE,
                                              stderr=subprocess.STDOUT, text=True)))
-    stub = os.path.join(EMU, "emu_lib_stubs.cpp")
-    obj = os.path.join(out_dir, "emu_lib_stubs.o")
-    objs.append(obj)
-    procs.append(("emu_lib_stubs.cpp", subprocess.Popen(["g++", *flags, "-c", stub, "-o", obj], stdout=subprocess.PIPE,
-                                                        stderr=subprocess.STDOUT, text=True)))
+    nccl_so = os.path.join(out_dir, "libfake_nccl.so")
+    procs.append(("fake_nccl.cpp", subprocess.Popen(["g++", *flags, "-I", EMU, "-shared", os.path.join(EMU, "fake_nccl.cpp"), "-o", nccl_so],
+                                                    stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for name, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"g++ failed for {name}:\n{out[-6000:]}")
     so = os.path.join(out_dir, "libcozo_gpu_emu.so")
-    r = subprocess.run(["g++", "-shared", "-pthread", *(["-fsanitize=address,undefined"] if sanitize else []), "-o", so, *objs],
+    r = subprocess.run(["g++", "-shared", "-pthread", *(["-fsanitize=address,undefined"] if sanitize else []), "-o", so, *objs, "-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-4000:])

@@ -128,9 +128,10 @@ template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiproces
   *n = (int)std::min<size_t>(std::min(by_smem, by_threads), 4);
   return cudaSuccess;
 }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+// "IPC": the ranks of an emulated group are threads of one process, so a handle is just the pointer
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 namespace emu {
 // dynamic shared memory of the running launch (`extern __shared__` declarations are rewritten to read this)

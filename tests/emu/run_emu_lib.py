@@ -357,8 +357,89 @@ def scenario_builder_fidelity():
         step(f"n={n} keep_pruned={keep} extend_candidates={extend}: {same} / {total} rows identical to the oracle builder's")
 
 
+def scenario_sharded():
+    """sharded.cu end to end with the ranks of a communicator as THREADS of this process (tests/emu/fake_nccl.cpp, CUDA IPC
+    handles = pointers): NCCL-form and fused peer-store exchange, tiling with double-buffered sets, host and device forms,
+    broadcast from a root, growth of the exchange buffers (close peers -> rendezvous -> reallocate), radius"""
+    import threading
+
+    from cozo_b200.sharded import merge_lists
+    os.environ["COZO_GPU_NCCL_LIB"] = os.path.join(os.path.dirname(capi.LIB_PATH), "libfake_nccl.so")
+    dim, m, k, ef, B = 24, 6, 5, 20, 37
+    Q = np.random.default_rng(7).random((B, dim), dtype=np.float32)
+    Qbig = np.random.default_rng(8).random((3 * B, dim), dtype=np.float32)
+    for world in (1, 2, 3, 8):
+        shards, rows = [], []
+        for r in range(world):
+            n = 110 + 25 * r                                           # ragged shards
+            X = np.random.default_rng(100 + r).random((n, dim), dtype=np.float32)
+            g = capi.HnswIndex.build(X, m=m, ef_construction=24, level_seed=5 + r)
+            ix = O.OracleHnsw.from_levels(X, O.HnswLevels(*g.export_levels()))
+            shards.append((g, ix))
+            rows.append(n)
+        offsets = np.cumsum([0] + rows[:-1])
+
+        def expected(Qx, kk, radius=None):
+            li = [g.search(Qx, kk, ef, radius=radius) for g, _ in shards]
+            oi = [ix.search(Qx, kk, ef, n_threads=2) for _, ix in shards]
+            e = merge_lists(np.stack([x[0] for x in li]), np.stack([x[1] for x in li]), offsets, kk)
+            o = merge_lists(np.stack([x[0] for x in oi]), np.stack([x[1] for x in oi]), offsets, kk)
+            return e, o, sum(int(x[3].dist_evals) for x in li)
+        (exp_i, exp_d), (orc_i, orc_d), _ = expected(Q, k)
+        assert np.array_equal(exp_i, orc_i) and np.allclose(exp_d, orc_d, rtol=1e-5)      # same sharding, same answer
+        (big_i, big_d), _, _ = expected(Qbig, k)
+        rad = float(np.median(exp_d[:, 3])) * (1 + 1e-4)
+        (rad_i, rad_d), _, _ = expected(Q, k, radius=rad)
+        seen = set()
+        for exchange in (1, 0):
+            for tile in (65536, 10):
+                capi.set_option("shard.exchange", exchange)
+                capi.set_option("shard.tile", tile)
+                uid = capi.ShardGroup.unique_id()
+                errors, infos = [], [None] * world
+
+                def rank_main(r):
+                    try:
+                        grp = capi.ShardGroup(uid, r, world)
+                        off, total = grp.attach(shards[r][0])
+                        assert off == int(offsets[r]) and total == sum(rows)
+                        for root in (-1, 0, world - 1):
+                            ids, dd, cnt, st = grp.search(Q if root in (-1, r) else None, k, ef, root=root, B=B)
+                            assert np.array_equal(ids, exp_i) and np.array_equal(dd, exp_d), (exchange, tile, root, r)
+                            assert np.all(cnt == k)
+                        infos[r] = grp.info()
+                        # device form, back to back (double-buffered sets), then a BIGGER batch: the exchange buffers grow
+                        oi_d, od_d = np.zeros((B, k), np.uint64), np.zeros((B, k), np.float32)
+                        for _ in range(3):
+                            grp.search_dev(Q.ctypes.data, B, k, ef, oi_d.ctypes.data, od_d.ctypes.data, None, None)
+                        assert np.array_equal(oi_d, exp_i) and np.array_equal(od_d, exp_d)
+                        ids, dd, _, _ = grp.search(Qbig, k, ef)
+                        assert np.array_equal(ids, big_i) and np.array_equal(dd, big_d)
+                        ids, dd, cnt, _ = grp.search(Q, k, ef, radius=rad)
+                        assert np.array_equal(ids, rad_i) and np.array_equal(cnt, (rad_d <= np.float32(rad)).sum(1))
+                        grp.close()
+                    except BaseException as e:           # noqa: BLE001
+                        import traceback
+                        errors.append(f"rank {r}: {e!r}\n{traceback.format_exc()}")
+                th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join(600)
+                assert not any(t.is_alive() for t in th), "a rank hangs"
+                assert not errors, "\n".join(errors)
+                assert len({i["exchange"] for i in infos}) == 1
+                seen.add(infos[0]["exchange"])
+        assert seen == {"fused", "nccl"}, seen
+        step(f"world {world}: host / device forms, roots, tiles of 65536 and 10, growth, radius == numpy merge of the per-shard "
+             f"lists == oracle under the same sharding; exchanges {sorted(seen)}")
+    capi.set_option("shard.exchange", 1)
+    capi.set_option("shard.tile", 65536)
+
+
 SCENARIOS = {"graph": scenario_graph, "pagerank": scenario_pagerank, "hnsw": scenario_hnsw,
-             "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity}
+             "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity,
+             "sharded": scenario_sharded}
 
 if __name__ == "__main__":
     capi.init(0)

@@ -4,8 +4,9 @@ through the same ctypes binding and checked against the same oracle as the `-m g
 
 Why: gpurun closed mid-round with several code paths never run on a GPU.  This runs ALL of them — the C ABI
 entry points, their host logic (staging, CUB sorts, launch geometry, chunking, option handling) and the kernels — with
-32-wide warps and real concurrency.  It is a logic check: no performance, no hardware memory model, no NCCL / IPC
-(sharded.cu is stubbed out).  The product never loads this library (tests/emu/run_emu_lib.py points the binding at it by
+32-wide warps and real concurrency.  It is a logic check: no performance, no hardware memory model.  NCCL and CUDA IPC
+are stand-ins whose ranks are threads of one process (tests/emu/fake_nccl.cpp), which is enough to run the sharded
+operator — fused peer stores, flag barrier and all — at world sizes 1, 2, 3 and 8.  The product never loads this library (tests/emu/run_emu_lib.py points the binding at it by
 hand, in a process of its own).  COZO_EMU_SANITIZE=1 builds with ASan + UBSan.
 
 The `-m gpu` test files themselves run against it too (tests/conftest.py honours COZO_EMU_LIB): the host-layer file and
@@ -44,7 +45,7 @@ def _run(lib, scenario, sm_count=4):
 
 
 def test_library_exports_every_abi_symbol(emu_lib):
-    """the emulated build is the whole ABI (the sharded entry points as stubs): same symbols as include/cozo_gpu.h"""
+    """the emulated build is the whole ABI: same symbols as include/cozo_gpu.h"""
     import ctypes
 
     from cozo_b200 import capi
@@ -63,6 +64,14 @@ def test_library_scenario(emu_lib, scenario, sm_count):
     sequential builder edge for edge."""
     out = _run(emu_lib, scenario, sm_count)
     print(out)
+
+
+def test_sharded_operator_with_rank_threads(emu_lib):
+    """cozo_gpu_shards_* / cozo_gpu_hnsw_*_sharded at world sizes 1, 2, 3, 8 (ranks = threads): both exchanges (one all-gather
+    per list; peer stores fused into the search epilogue + flag barrier), tiles with double-buffered sets, host and device
+    forms, broadcast roots, growth of the exchange buffers, radius == numpy merge of the per-shard lists == the oracle under
+    the same sharding"""
+    print(_run(emu_lib, "sharded"))
 
 
 def _pytest_on_emu(lib, args, timeout):
