@@ -100,6 +100,10 @@ struct cozo_gpu_shards {
   uint32_t* local_ids[2] = {nullptr, nullptr};   // NCCL form: the all-gather's send buffers
   float* local_dist[2] = {nullptr, nullptr};
   uint32_t epoch = 0;
+  // running tile counter: consecutive tiles — of one call or of consecutive calls — alternate between the two
+  // buffer sets.  A rank may only overwrite a peer's set once that peer has merged what the set held; passing the
+  // barrier of tile i proves every peer has finished merging tile i-1 (stream order on the peer), i.e. the OTHER set.
+  uint32_t tile_seq = 0;
   int* d_timeout = nullptr;
   // staging of the host-pointer call
   float* d_q = nullptr;
@@ -188,6 +192,7 @@ static int ensure_exchange(cozo_gpu_shards* s, uint32_t tile, uint32_t k) {
   COZO_CUDA(cudaMalloc(&s->block, s->block_bytes));
   COZO_CUDA(cudaMemsetAsync(s->block, 0, 256, s->stream));  // ordered before the handle exchange below
   s->epoch = 0;
+  s->tile_seq = 0;
   for (int b = 0; b < 2; ++b) {
     COZO_CUDA(cudaMalloc(&s->local_ids[b], (size_t)tile * k * 4));
     COZO_CUDA(cudaMalloc(&s->local_dist[b], (size_t)tile * k * 4));
@@ -265,9 +270,9 @@ static int sharded_search_dev(cozo_gpu_shards* s, const float* d_q, uint32_t B, 
   int rc = ensure_exchange(s, tile, k);
   if (rc) return rc;
   cudaStream_t st = s->stream;
-  for (uint32_t q0 = 0, t = 0; q0 < B; q0 += tile, ++t) {
+  for (uint32_t q0 = 0; q0 < B; q0 += tile) {
     const uint32_t nq = std::min(tile, B - q0);
-    const int b = (int)(t & 1);
+    const int b = (int)(s->tile_seq++ & 1u);  // NOT the tile index of this call: back-to-back single-tile calls must alternate too
     const float* q = d_q + (size_t)q0 * dim;
     uint32_t* qs = d_qstats ? d_qstats + (size_t)q0 * 4 : nullptr;
     if (s->exchange == 1) {

@@ -242,7 +242,13 @@ template <class T> inline T __ldcg(const T* p) { return *reinterpret_cast<const 
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
-inline void __nanosleep(unsigned) { emu::lane_yield(); }
+// a polite spin: let the sibling lanes run, and every so often give the core away — a warp whose lanes all poll a flag
+// that another rank / warp has yet to write must not starve that writer on a loaded machine
+inline void __nanosleep(unsigned) {
+  static thread_local unsigned polls = 0;
+  emu::lane_yield();
+  if ((++polls & 1023u) == 0) std::this_thread::sleep_for(std::chrono::microseconds(50));
+}
 inline void __trap() { std::fprintf(stderr, "emu: __trap()\n"); std::abort(); }
 inline long long clock64() { return std::chrono::steady_clock::now().time_since_epoch().count(); }
 using std::isfinite;
