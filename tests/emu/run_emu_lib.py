@@ -368,7 +368,7 @@ def scenario_sharded():
     dim, m, k, ef, B = 24, 6, 5, 20, 37
     Q = np.random.default_rng(7).random((B, dim), dtype=np.float32)
     Qbig = np.random.default_rng(8).random((3 * B, dim), dtype=np.float32)
-    for world in (1, 2, 3, 8):
+    for world in ((1, 2, 3, 8) if (os.cpu_count() or 1) >= 8 else (1, 2, 3)):     # 8 = the driver's scaling run
         shards, rows = [], []
         for r in range(world):
             n = 110 + 25 * r                                           # ragged shards

@@ -9,7 +9,9 @@ round-end `pytest -m gpu` does not select them, and they skip unless COZO_RUN_UN
 
     COZO_RUN_UNVERIFIED=1 python -m pytest tests/test_unverified_gpu.py -q
 
-The layout logic of the PageRank engine is additionally covered on the CPU by tests/test_pagerank_model_cpu.py.
+The layout logic of the PageRank engine is additionally covered on the CPU by tests/test_pagerank_model_cpu.py, and this
+whole file passes (12 / 12) against the CPU-emulated build of the library (tests/test_emu_lib_cpu.py; record in
+profiles/r02_emu_gpu_testfiles.txt) — which is how the extend_candidates interleaving bug was found and fixed.
 """
 import os
 
