@@ -437,9 +437,123 @@ def scenario_sharded():
     capi.set_option("shard.tile", 65536)
 
 
+FUZZ_N = int(os.environ.get("COZO_EMU_FUZZ", 40))
+
+
+def scenario_fuzz_hnsw():
+    """differential fuzzing of build + search against the oracle on the exported graph: random sizes (1..129 rows), dims
+    (1..130, padded and unpadded), metrics, m, ef_construction, k, ef, batch, search mode, duplicates (distance ties),
+    radius, filter mask; the expected list is the oracle's ef candidates put through the reference's post-processing"""
+    N, seed0 = FUZZ_N, 1000
+    fails = 0
+    for case in range(N):
+        rng = np.random.default_rng(seed0 + case)
+        n = int(rng.integers(1, 130)); dim = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16, 17, 31, 32, 33, 48, 100, 130]))
+        metric = int(rng.integers(0, 3)); m = int(rng.integers(2, 9)); efc = int(rng.integers(2, 40))
+        k = int(rng.integers(1, 16)); ef = int(rng.integers(1, 40)); B = int(rng.integers(1, 12))
+        keep = bool(rng.integers(0, 2)); mode = int(rng.choice([-1, 0, 1, 2]))
+        X = (rng.random((n, dim), dtype=np.float32) - 0.5)
+        if rng.random() < 0.2 and n > 4:       # duplicates -> distance ties
+            X[n // 2:] = X[: n - n // 2]
+        if metric == 1: X += 0.01            # no zero vectors for cosine
+        Q = (rng.random((B, dim), dtype=np.float32) - 0.5)
+        desc = dict(n=n, dim=dim, metric=metric, m=m, efc=efc, k=k, ef=ef, B=B, keep=keep, mode=mode, seed=seed0 + case)
+        try:
+            g = capi.HnswIndex.build(X, metric=metric, m=m, ef_construction=efc, keep_pruned_connections=keep, level_seed=case)
+            lv = g.export_levels()
+            ix = O.OracleHnsw.from_levels(X, O.HnswLevels(*lv), metric=metric)
+            use_r = rng.random() < 0.3
+            oi, od, oc, ost = ix.search(Q, k, ef, n_threads=1)
+            radius = None
+            if use_r and oc.min() > 0:
+                radius = float(np.median(od[:, 0])) * 1.5 + 1e-3 if np.median(od[:, 0]) > 0 else None
+            use_f = rng.random() < 0.3
+            row_pass = (rng.random(n) < 0.5) if use_f else None
+            capi.set_option("hnsw.mode", mode)
+            gi, gd, gc, st = g.search(Q, k, ef, radius=radius, row_pass=row_pass)
+            capi.set_option("hnsw.mode", -1)
+            fi, fd, fc, _ = ix.search(Q, ef, ef, n_threads=1)     # all candidates, then the reference's post-processing
+            for q in range(B):
+                cand = [(int(i), float(d)) for i, d in zip(fi[q, :fc[q]], fd[q, :fc[q]])]
+                if radius is not None: cand = [c for c in cand if c[1] <= radius]
+                if row_pass is not None: cand = [c for c in cand if row_pass[c[0]]]
+                cand = cand[:k]
+                got = [(int(i), float(d)) for i, d in zip(gi[q, :gc[q]], gd[q, :gc[q]])]
+                ok = len(got) == len(cand) and all(abs(a[1] - b[1]) <= 1e-5 * max(1, abs(b[1])) + 1e-6 for a, b in zip(got, cand))
+                # ids may swap inside an exact distance tie; compare as multisets of (rounded dist) and sets when no ties
+                if ok and [a[0] for a in got] != [b[0] for b in cand]:
+                    ds = [round(b[1], 6) for b in cand]
+                    ok = len(set(ds)) < len(ds) or (radius is not None and any(abs(b[1] / radius - 1) < 1e-5 for b in cand))
+                if not ok:
+                    fails += 1
+                    print('MISMATCH', desc, 'q', q, 'got', got[:6], 'exp', cand[:6], flush=True)
+                    break
+        except Exception as e:
+            fails += 1
+            print('ERROR', desc, repr(e), flush=True)
+    
+    assert fails == 0, fails
+    step(f"{N} random index / query configurations: 0 mismatches")
+
+
+def scenario_fuzz_graph():
+    """differential fuzzing of the graph rules: random multigraphs (self loops, duplicate edges, isolated nodes, zero
+    weights), SSSP in the three frontier forms, closeness, betweenness, PageRank in both engines with random blocking
+    geometries, clustering — all against the oracle"""
+    N, seed0, fails = FUZZ_N, 5000, 0
+    for case in range(N):
+        rng = np.random.default_rng(seed0 + case)
+        n = int(rng.integers(1, 90)); m = int(rng.integers(0, 6 * n + 1))
+        src = rng.integers(0, n, m).astype(np.uint32); dst = rng.integers(0, n, m).astype(np.uint32)
+        kind = int(rng.integers(0, 3))
+        w = [(rng.integers(0, 8, m) / 4).astype(np.float32), (rng.random(m) * 5).astype(np.float32), (rng.integers(1, 64, m) / 8).astype(np.float32)][kind]
+        desc = dict(n=n, m=m, kind=kind, seed=seed0 + case)
+        try:
+            g = capi.Graph(n, src, dst, w); o = O.OracleGraph(n, src, dst, w)
+            srcs = rng.integers(0, n, int(rng.integers(1, 6))).astype(np.uint32)
+            od, _ = o.sssp(srcs)
+            for opt in (None, "sssp.frontier", "sssp.wide"):
+                if opt: capi.set_option(opt, 1)
+                gd, gp, _ = g.sssp(srcs)
+                if opt: capi.set_option(opt, 0)
+                if not np.array_equal(gd, od):
+                    fails += 1; print('SSSP MISMATCH', desc, opt, flush=True)
+            oc = o.closeness(); gc, _ = g.closeness()
+            fin = np.isfinite(oc)
+            if not (np.array_equal(np.isfinite(gc), fin) and np.allclose(gc[fin], oc[fin], rtol=1e-5)):
+                fails += 1; print('CLOSENESS MISMATCH', desc, flush=True)
+            if kind == 2:     # strictly positive weights: betweenness well defined
+                ob = o.betweenness(); gb, _ = g.betweenness()
+                if not np.allclose(gb, ob, rtol=1e-4, atol=1e-6):
+                    fails += 1; print('BETWEENNESS MISMATCH', desc, np.max(np.abs(gb - ob)), flush=True)
+            gu = capi.Graph(n, src, dst); ou = O.OracleGraph(n, src, dst)
+            it = int(rng.integers(1, 8))
+            os_, oit, _ = ou.pagerank(0.85, 0.0, it)
+            for mode in (0, 1):
+                capi.set_option("pagerank.mode", mode)
+                if mode:
+                    capi.set_option("pagerank.hub_slots", int(rng.choice([0, 4, 8, 64])))
+                    capi.set_option("pagerank.group_slots", int(rng.choice([64, 128, 256])))
+                    capi.set_option("pagerank.window", int(rng.choice([64, 97, 512])))
+                    capi.set_option("pagerank.chunk", 1024)
+                gs, git, _, _ = gu.pagerank(0.85, 0.0, it)
+                if git != oit or (n and np.max(np.abs(gs - os_) / os_) > 1e-5):
+                    fails += 1; print('PAGERANK MISMATCH', desc, mode, flush=True)
+            capi.set_option("pagerank.mode", 0)
+            ms, md = np.concatenate([src, dst]), np.concatenate([dst, src])
+            a = capi.Graph(n, ms, md).clustering(); b = O.OracleGraph(n, ms, md).clustering()
+            if not (np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])):
+                fails += 1; print('CLUSTERING MISMATCH', desc, flush=True)
+        except Exception as e:
+            fails += 1; print('ERROR', desc, repr(e), flush=True)
+    
+    assert fails == 0, fails
+    step(f"{N} random graphs: 0 mismatches")
+
+
 SCENARIOS = {"graph": scenario_graph, "pagerank": scenario_pagerank, "hnsw": scenario_hnsw,
              "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity,
-             "sharded": scenario_sharded}
+             "sharded": scenario_sharded, "fuzz_hnsw": scenario_fuzz_hnsw, "fuzz_graph": scenario_fuzz_graph}
 
 if __name__ == "__main__":
     capi.init(0)

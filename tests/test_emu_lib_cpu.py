@@ -66,6 +66,12 @@ def test_library_scenario(emu_lib, scenario, sm_count):
     print(out)
 
 
+@pytest.mark.parametrize("scenario", ["fuzz_hnsw", "fuzz_graph"])
+def test_differential_fuzzing(emu_lib, scenario):
+    """random configurations against the oracle (COZO_EMU_FUZZ=<n> cases per family, default 40; 150 + 120 were run clean)"""
+    print(_run(emu_lib, scenario))
+
+
 def test_sharded_operator_with_rank_threads(emu_lib):
     """cozo_gpu_shards_* / cozo_gpu_hnsw_*_sharded at world sizes 1, 2, 3, 8 (ranks = threads): both exchanges (one all-gather
     per list; peer stores fused into the search epilogue + flag barrier), tiles with double-buffered sets, host and device
