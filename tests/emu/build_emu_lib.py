@@ -118,10 +118,12 @@ def transform(name: str, src: str) -> str:
     return f'// GENERATED from cozo_b200/csrc/{name} by tests/emu/build_emu_lib.py — do not edit\n#line 1 "{os.path.join(CSRC, name)}"\n' + src
 
 
-def build(out_dir: str, sanitize: bool = False) -> str:
+def build(out_dir: str, sanitize: bool = False, lane_threads: bool = False) -> str:
     os.makedirs(out_dir, exist_ok=True)
     flags = ["-std=c++20", "-O1", "-g", "-fPIC", "-pthread", "-DCOZO_CPU_EMU_LIB", "-Wno-unused-value",
              "-I", os.path.join(EMU, "fake_cuda"), "-I", CSRC]
+    if lane_threads:      # one OS thread per lane instead of fibers: every lane truly concurrent, 50-100x slower
+        flags.append("-DCOZO_EMU_LANE_THREADS")
     if sanitize:
         flags += ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
     objs, procs = [], []
@@ -151,4 +153,5 @@ def build(out_dir: str, sanitize: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(sys.argv[1] if len(sys.argv) > 1 else "/tmp/cozo_emu_lib", sanitize="--sanitize" in sys.argv))
+    print(build(sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "/tmp/cozo_emu_lib",
+                sanitize="--sanitize" in sys.argv, lane_threads="--lane-threads" in sys.argv))
