@@ -426,6 +426,12 @@ static int pr_stage_pb(PrState* st, uint32_t NH, uint32_t GS, uint32_t WIN) {
   st->NH = NH = std::min(NH, n);
   st->GS = GS;
   st->WIN = WIN;
+  // a handle may be re-staged with another geometry: nothing derived from the previous one may survive an early return
+  // (the all-hub case below used to leave n_items / Mpad of the old blocking behind -> K_A launched on freed tables)
+  st->n_items = 0;
+  st->Mpad = 0;
+  st->G = st->NB = 0;
+  st->Htot = st->Mtot = 0;
   P_CUDA(cudaMalloc(&st->hptr, np1 * 4));
   P_CUDA(cudaMalloc(&st->mptr, np1 * 4));
   pb_row_split_kernel<<<(uint32_t)((np1 + 255) / 256), 256>>>(st->in_ptr, st->in_idx, n, NH, st->hptr, st->mptr);

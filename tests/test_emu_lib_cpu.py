@@ -72,6 +72,12 @@ def test_differential_fuzzing(emu_lib, scenario):
     print(_run(emu_lib, scenario))
 
 
+def test_sanitizer_workload(emu_lib):
+    """tools/sanitize.py (every kernel on tiny inputs, option sweeps on one staged graph) runs to the end: this is the run
+    that exposed the stale blocking state of a re-staged PageRank graph"""
+    print(_run(emu_lib, "sanitize_workload"))
+
+
 def test_sharded_operator_with_rank_threads(emu_lib):
     """cozo_gpu_shards_* / cozo_gpu_hnsw_*_sharded at world sizes 1, 2, 3, 8 (ranks = threads): both exchanges (one all-gather
     per list; peer stores fused into the search epilogue + flag barrier), tiles with double-buffered sets, host and device
