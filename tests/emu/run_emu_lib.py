@@ -612,10 +612,66 @@ def scenario_sanitize_workload():
     step("tools/sanitize.py ran to the end")
 
 
+def scenario_fuzz_sequences():
+    """random API sequences on one handle — built, or staged from an export like the glue does — insert / remove / update with
+    a search of random shape (k, ef, batch, mode, filter) after every step: results and traversal counters == oracle on the
+    exported graph, no removed id ever returned (exercises workspace regrowth and the lazily derived build state)"""
+    N, fails = max(1, FUZZ_N // 2), 0
+    for case in range(N):
+        rng = np.random.default_rng(31000 + case)
+        dim = int(rng.choice([4, 9, 32, 130])); m = int(rng.integers(2, 9)); efc = int(rng.integers(4, 40)); metric = int(rng.integers(0, 3))
+        pool = rng.random((600, dim), dtype=np.float32) - 0.5 + (0.01 if metric == 1 else 0)
+        n0 = int(rng.integers(1, 80)); X = pool[:n0].copy(); nxt = n0; live = np.ones(n0, bool)
+        desc = dict(case=case, dim=dim, m=m, efc=efc, metric=metric, n0=n0)
+        try:
+            staged = rng.random() < 0.4
+            g = capi.HnswIndex.build(X, metric=metric, m=m, ef_construction=efc, level_seed=case)
+            if staged:      # continue on a handle staged from the export (the glue's path)
+                ni, rp, ci, ep = g.export_levels()
+                g = capi.HnswIndex.stage(X, ni, rp, ci, ep, metric=metric, m_max0=2 * m, m_max=m)
+            for op in range(int(rng.integers(3, 10))):
+                kind = int(rng.integers(0, 5)); n = len(X)
+                if kind == 0:
+                    c = int(rng.integers(1, 40)); first = g.insert(pool[nxt:nxt + c], ef_construction=efc); assert first == n
+                    X = np.concatenate([X, pool[nxt:nxt + c]]); live = np.concatenate([live, np.ones(c, bool)]); nxt += c
+                elif kind == 1 and live.sum() > 2:
+                    ids = rng.choice(np.flatnonzero(live), size=int(rng.integers(1, max(2, live.sum() // 2))), replace=False).astype(np.uint32)
+                    g.remove(ids); live[ids] = False
+                elif kind == 2:
+                    ids = rng.choice(n, size=int(rng.integers(1, min(n, 8) + 1)), replace=False).astype(np.uint32)
+                    g.update(ids, pool[nxt:nxt + len(ids)], ef_construction=efc); X[ids] = pool[nxt:nxt + len(ids)]; live[ids] = True; nxt += len(ids)
+                if not live.any():
+                    continue
+                # a search with random shape after every step (workspace regrowth, all modes, filter, radius)
+                k = int(rng.integers(1, 20)); ef = int(rng.integers(1, 60)); B = int(rng.integers(1, 40)); mode = int(rng.choice([-1, 0, 1, 2]))
+                Q = rng.random((B, dim), dtype=np.float32) - 0.5
+                ni, rp, ci, ep = g.export_levels()
+                ix = O.OracleHnsw.from_levels(X, O.HnswLevels(ni, rp, ci, ep), metric=metric)
+                row_pass = (rng.random(len(X)) < 0.6) if rng.random() < 0.4 else None
+                capi.set_option("hnsw.mode", mode)
+                gi, gd, gc, st = g.search(Q, k, ef, row_pass=row_pass)
+                capi.set_option("hnsw.mode", -1)
+                fi, fd, fc, ost = ix.search(Q, ef, ef, n_threads=1)
+                assert st.dist_evals == int(ost[:, 0].sum()), ('counters', st.dist_evals, int(ost[:, 0].sum()))
+                for q in range(B):
+                    cand = [(int(i), float(d)) for i, d in zip(fi[q, :fc[q]], fd[q, :fc[q]])]
+                    if row_pass is not None: cand = [c for c in cand if row_pass[c[0]]]
+                    cand = cand[:k]
+                    got = [(int(i), float(d)) for i, d in zip(gi[q, :gc[q]], gd[q, :gc[q]])]
+                    assert len(got) == len(cand) and all(abs(a[1] - b[1]) <= 1e-5 * max(1, abs(b[1])) + 1e-6 for a, b in zip(got, cand)), ('search', op, q, got[:4], cand[:4])
+                    assert all(live[i] for i, _ in got)
+        except Exception as e:
+            fails += 1; print('FAIL', desc, repr(e)[:400], flush=True)
+    
+    assert fails == 0, fails
+    step(f"{N} random API sequences: 0 failures")
+
+
 SCENARIOS = {"graph": scenario_graph, "pagerank": scenario_pagerank, "hnsw": scenario_hnsw,
              "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity,
              "sharded": scenario_sharded, "fuzz_hnsw": scenario_fuzz_hnsw, "fuzz_graph": scenario_fuzz_graph,
-             "fuzz_maintenance": scenario_fuzz_maintenance, "sanitize_workload": scenario_sanitize_workload}
+             "fuzz_maintenance": scenario_fuzz_maintenance, "sanitize_workload": scenario_sanitize_workload,
+             "fuzz_sequences": scenario_fuzz_sequences}
 
 if __name__ == "__main__":
     capi.init(0)
