@@ -667,11 +667,58 @@ def scenario_fuzz_sequences():
     step(f"{N} random API sequences: 0 failures")
 
 
+def scenario_fuzz_sharded():
+    """random communicators (1-4 rank threads, shards of 1-89 rows, metrics), exchanges, tiles (1, 3, 7, 65536) and call
+    sequences with random batch / k / ef / root: the operator's result == numpy merge of the per-shard lists on every rank"""
+    import threading
+
+    from cozo_b200.sharded import merge_lists
+    os.environ["COZO_GPU_NCCL_LIB"] = os.path.join(os.path.dirname(capi.LIB_PATH), "libfake_nccl.so")
+    N, fails = max(1, FUZZ_N // 4), 0
+    for case in range(N):
+        rng = np.random.default_rng(4400 + case)
+        world = int(rng.integers(1, 5)); dim = int(rng.choice([3, 16, 33])); metric = int(rng.integers(0, 3))
+        shards, rows = [], []
+        for r in range(world):
+            n = int(rng.integers(1, 90))
+            X = rng.random((n, dim), dtype=np.float32) - 0.5 + (0.01 if metric == 1 else 0)
+            shards.append(capi.HnswIndex.build(X, metric=metric, m=4, ef_construction=16, level_seed=case * 10 + r)); rows.append(n)
+        offsets = np.cumsum([0] + rows[:-1])
+        exchange = int(rng.integers(0, 2)); tile = int(rng.choice([1, 3, 7, 65536]))
+        capi.set_option("shard.exchange", exchange); capi.set_option("shard.tile", tile)
+        calls = []
+        for _ in range(int(rng.integers(1, 5))):
+            B = int(rng.integers(1, 30)); k = int(rng.integers(1, 12)); ef = int(rng.integers(1, 30))
+            Q = rng.random((B, dim), dtype=np.float32) - 0.5
+            li = [g.search(Q, k, ef) for g in shards]
+            calls.append((Q, k, ef, merge_lists(np.stack([x[0] for x in li]), np.stack([x[1] for x in li]), offsets, k), int(rng.integers(-1, world))))
+        uid = capi.ShardGroup.unique_id(); errs = []
+        def rank_main(r):
+            try:
+                grp = capi.ShardGroup(uid, r, world); grp.attach(shards[r])
+                for Q, k, ef, (ei, ed), root in calls:
+                    ids, dd, cnt, _ = grp.search(Q if root in (-1, r) else None, k, ef, root=root, B=len(Q))
+                    assert np.array_equal(ids, ei) and np.array_equal(dd, ed), (r, root)
+                    assert np.array_equal(cnt, (ei != np.uint64(0xFFFFFFFFFFFFFFFF)).sum(1))
+                grp.close()
+            except BaseException as e:
+                errs.append(repr(e)[:300])
+        th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        [t.start() for t in th]; [t.join(300) for t in th]
+        if errs or any(t.is_alive() for t in th):
+            fails += 1; print('FAIL', dict(case=case, world=world, dim=dim, metric=metric, exchange=exchange, tile=tile, rows=rows), errs[:2], flush=True)
+    
+    capi.set_option("shard.exchange", 1)
+    capi.set_option("shard.tile", 65536)
+    assert fails == 0, fails
+    step(f"{N} random sharded configurations: 0 failures")
+
+
 SCENARIOS = {"graph": scenario_graph, "pagerank": scenario_pagerank, "hnsw": scenario_hnsw,
              "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity,
              "sharded": scenario_sharded, "fuzz_hnsw": scenario_fuzz_hnsw, "fuzz_graph": scenario_fuzz_graph,
              "fuzz_maintenance": scenario_fuzz_maintenance, "sanitize_workload": scenario_sanitize_workload,
-             "fuzz_sequences": scenario_fuzz_sequences}
+             "fuzz_sequences": scenario_fuzz_sequences, "fuzz_sharded": scenario_fuzz_sharded}
 
 if __name__ == "__main__":
     capi.init(0)
