@@ -69,14 +69,14 @@ capi.set_option("hnsw.mode", -1)
 ni, rp, ci, ep = g.export_levels()
 g64 = capi.HnswIndex.stage(X.astype(np.float64), ni, rp, ci, ep, m_max0=16, m_max=8)
 g64.search_f64(Q.astype(np.float64), 5, 40, row_pass=rng.random(1500) < 0.5)
-capi.set_option("sssp.force_queue", 1)
+capi.set_option("sssp.frontier", 1)
 gg.sssp(np.arange(0, 300, 50, dtype=np.uint32))
 gg.closeness()
-capi.set_option("sssp.force_queue", 0)
+capi.set_option("sssp.frontier", 0)
 capi.set_option("sssp.wide", 1)
 gg.sssp(np.arange(0, 300, 100, dtype=np.uint32))
 gg.sssp_paths(np.array([0, 5], np.uint32), np.array([7, 9], np.uint32), forb_nodes=[[3], []], forb_edges=[[], [(5, 9)]])
-capi.set_option("sssp.wide", -1)
+capi.set_option("sssp.wide", 0)
 for exch in (1, 0):
     capi.set_option("shard.exchange", exch)
     capi.set_option("shard.tile", 16)
