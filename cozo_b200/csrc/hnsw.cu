@@ -556,10 +556,19 @@ extern "C" int cozo_gpu_hnsw_stage(cozo_gpu_hnsw_t** out, const CozoGpuHnswStage
   g.top_level = d->n_levels - 1;
 
   // strides: observed max degree, at least the manifest bound
+  // (row pointers come from the caller: a decreasing pair would wrap into an absurd stride below)
+  constexpr uint32_t kMaxStagedDegree = 65536;
   uint32_t maxdeg0 = d->m_max0;
   {
     const CozoGpuHnswLevel& l0 = d->levels[0];
-    for (uint32_t i = 0; i < n; ++i) maxdeg0 = std::max<uint32_t>(maxdeg0, (uint32_t)(l0.row_ptr[i + 1] - l0.row_ptr[i]));
+    for (uint32_t i = 0; i < n; ++i) {
+      if (l0.row_ptr[i + 1] < l0.row_ptr[i] || l0.row_ptr[i + 1] - l0.row_ptr[i] > kMaxStagedDegree) {
+        delete h;
+        return set_error(COZO_GPU_EINVAL, "layer 0: row_ptr must be non-decreasing with at most %u neighbours per row (row %u)",
+                         kMaxStagedDegree, i);
+      }
+      maxdeg0 = std::max<uint32_t>(maxdeg0, (uint32_t)(l0.row_ptr[i + 1] - l0.row_ptr[i]));
+    }
   }
   uint32_t maxdegu = d->m_max;
   for (uint32_t L = 1; L < d->n_levels; ++L) {
@@ -568,8 +577,14 @@ extern "C" int cozo_gpu_hnsw_stage(cozo_gpu_hnsw_t** out, const CozoGpuHnswStage
       delete h;
       return set_error(COZO_GPU_EINVAL, "layer -%u needs node_ids", L);
     }
-    for (uint32_t i = 0; i < lv.n_nodes; ++i)
+    for (uint32_t i = 0; i < lv.n_nodes; ++i) {
+      if (lv.row_ptr[i + 1] < lv.row_ptr[i] || lv.row_ptr[i + 1] - lv.row_ptr[i] > kMaxStagedDegree) {
+        delete h;
+        return set_error(COZO_GPU_EINVAL, "layer -%u: row_ptr must be non-decreasing with at most %u neighbours per row (row %u)", L,
+                         kMaxStagedDegree, i);
+      }
       maxdegu = std::max<uint32_t>(maxdegu, (uint32_t)(lv.row_ptr[i + 1] - lv.row_ptr[i]));
+    }
   }
   g.s0 = round_up(std::max(maxdeg0, 1u), 32);
   g.su = round_up(std::max(maxdegu, 1u), 32);

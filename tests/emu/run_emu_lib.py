@@ -714,11 +714,91 @@ def scenario_fuzz_sharded():
     step(f"{N} random sharded configurations: 0 failures")
 
 
+def scenario_misuse():
+    """edge cases and misuse of every handle type: each call either works or returns a cozo_gpu error code — never a crash
+    (run it with COZO_EMU_SANITIZE=1 for the memory-safety half of that statement)"""
+    os.environ["COZO_GPU_NCCL_LIB"] = os.path.join(os.path.dirname(capi.LIB_PATH), "libfake_nccl.so")
+    rng = np.random.default_rng(0)
+    def expect_err(name, fn, codes=None):
+        try:
+            fn()
+        except capi.CozoGpuError as e:
+            assert codes is None or e.code in codes, (name, e.code, str(e))
+            print(f"  {name}: error {e.code} ok")
+            return
+        except (AssertionError, ValueError, TypeError, AttributeError) as e:
+            print(f"  {name}: python-level {type(e).__name__} ok"); return
+        raise AssertionError(f"{name}: accepted")
+    def ok(name, fn):
+        r = fn(); print(f"  {name}: ok"); return r
+    X = rng.random((50, 8), dtype=np.float32)
+    g = capi.HnswIndex.build(X, m=4, ef_construction=10)
+    Q = rng.random((3, 8), dtype=np.float32)
+    expect_err("k=0", lambda: g.search(Q, 0, 10))
+    expect_err("ef=0", lambda: g.search(Q, 3, 0))
+    ok("B=0", lambda: g.search(np.zeros((0, 8), np.float32), 3, 10))
+    ok("k > n", lambda: g.search(Q, 500, 600))
+    expect_err("huge ef (beyond shared memory)", lambda: g.search(Q, 3, 100000), codes=(capi.E_UNSUP,))
+    ok("large ef", lambda: g.search(Q, 3, 5000))
+    expect_err("remove out of range", lambda: g.remove(np.array([50], np.uint32)))
+    ok("remove nothing", lambda: g.remove(np.zeros(0, np.uint32)))
+    ok("remove twice", lambda: (g.remove(np.array([3], np.uint32)), g.remove(np.array([3], np.uint32))))
+    expect_err("update duplicate ids", lambda: g.update(np.array([1, 1], np.uint32), X[:2]))
+    expect_err("update out of range", lambda: g.update(np.array([99], np.uint32), X[:1]))
+    ok("insert nothing", lambda: g.insert(np.zeros((0, 8), np.float32)))
+    ok("remove everything then search", lambda: (g.remove(np.flatnonzero(g.export_live()).astype(np.uint32)), g.search(Q, 3, 10)))
+    ok("insert after removing everything", lambda: (g.insert(X[:5]), g.search(Q, 3, 10)))
+    expect_err("m = 1", lambda: capi.HnswIndex.build(X, m=1, ef_construction=10))
+    expect_err("m = 65", lambda: capi.HnswIndex.build(X, m=65, ef_construction=10))
+    expect_err("efc = 0", lambda: capi.HnswIndex.build(X, m=4, ef_construction=0))
+    expect_err("metric 7", lambda: capi.HnswIndex.build(X, metric=7, m=4, ef_construction=10))
+    ok("one vector", lambda: capi.HnswIndex.build(X[:1], m=4, ef_construction=10).search(Q, 3, 10))
+    ni, rp, ci, ep = capi.HnswIndex.build(X, m=4, ef_construction=10).export_levels()
+    bad = [c.copy() for c in ci]; bad[0][0] = 4000
+    expect_err("stage: neighbour out of range", lambda: capi.HnswIndex.stage(X, ni, rp, bad, ep, m_max0=8, m_max=4))
+    badrp = [r.copy() for r in rp]; badrp[0][3] = badrp[0][2] - 1 if badrp[0][2] > 0 else 7
+    expect_err("stage: row_ptr not monotone", lambda: capi.HnswIndex.stage(X, ni, badrp, ci, ep, m_max0=8, m_max=4))
+    expect_err("stage: entry out of range", lambda: capi.HnswIndex.stage(X, ni, rp, ci, 999, m_max0=8, m_max=4))
+    g64 = capi.HnswIndex.stage(X.astype(np.float64), ni, rp, ci, ep, m_max0=8, m_max=4)
+    expect_err("f32 search on F64", lambda: g64.search(Q, 3, 10))
+    expect_err("insert on F64", lambda: g64.insert(X[:2]))
+    gf = capi.HnswIndex.stage(X, ni, rp, ci, ep, m_max0=8, m_max=4)
+    expect_err("f64 search on F32", lambda: gf.search_f64(Q.astype(np.float64), 3, 10))
+    # graphs
+    e = np.zeros(0, np.uint32)
+    g0 = capi.Graph(0, e, e)
+    ok("n=0 pagerank", g0.pagerank); ok("n=0 closeness", g0.closeness); ok("n=0 betweenness", g0.betweenness); ok("n=0 clustering", g0.clustering)
+    ok("n=0 sssp no sources", lambda: g0.sssp(e))
+    g1 = capi.Graph(5, np.array([0, 1], np.uint32), np.array([1, 2], np.uint32), np.array([1, 2], np.float32))
+    expect_err("sssp source out of range", lambda: g1.sssp(np.array([5], np.uint32)))
+    expect_err("pagerank iterations 0", lambda: g1.pagerank(0.85, 1e-4, 0))
+    expect_err("paths max_len 0", lambda: g1.sssp_paths(np.array([0], np.uint32), np.array([2], np.uint32), max_len=0))
+    expect_err("paths goal out of range", lambda: g1.sssp_paths(np.array([0], np.uint32), np.array([9], np.uint32)))
+    ok("paths unreachable", lambda: g1.sssp_paths(np.array([2], np.uint32), np.array([0], np.uint32)))
+    ok("self loops only", lambda: capi.Graph(3, np.array([0, 1, 2], np.uint32), np.array([0, 1, 2], np.uint32)).betweenness())
+    for mode in (0, 1):
+        capi.set_option("pagerank.mode", mode)
+        ok(f"pagerank mode {mode} self loops", lambda: capi.Graph(3, np.array([0, 1, 2], np.uint32), np.array([0, 1, 2], np.uint32)).pagerank(0.85, 0.0, 3))
+        ok(f"pagerank mode {mode} one node", lambda: capi.Graph(1, e, e).pagerank(0.85, 0.0, 3))
+    capi.set_option("pagerank.mode", 0)
+    # shards
+    expect_err("shards rank out of range", lambda: capi.ShardGroup(capi.ShardGroup.unique_id(), 3, 2))
+    expect_err("shards world 17", lambda: capi.ShardGroup(capi.ShardGroup.unique_id(), 0, 17))
+    grp = capi.ShardGroup(capi.ShardGroup.unique_id(), 0, 1)
+    expect_err("sharded search before attach", lambda: grp.search(Q, 3, 10))
+    grp.attach(gf)
+    expect_err("sharded k=0", lambda: grp.search(Q, 0, 10))
+    ok("sharded B=0", lambda: grp.search(np.zeros((0, 8), np.float32), 3, 10))
+    ok("sharded k > rows", lambda: grp.search(Q, 200, 300))
+    grp.close()
+    step("every misuse answered with an error code, every edge case served")
+
+
 SCENARIOS = {"graph": scenario_graph, "pagerank": scenario_pagerank, "hnsw": scenario_hnsw,
              "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity,
              "sharded": scenario_sharded, "fuzz_hnsw": scenario_fuzz_hnsw, "fuzz_graph": scenario_fuzz_graph,
              "fuzz_maintenance": scenario_fuzz_maintenance, "sanitize_workload": scenario_sanitize_workload,
-             "fuzz_sequences": scenario_fuzz_sequences, "fuzz_sharded": scenario_fuzz_sharded}
+             "fuzz_sequences": scenario_fuzz_sequences, "fuzz_sharded": scenario_fuzz_sharded, "misuse": scenario_misuse}
 
 if __name__ == "__main__":
     capi.init(0)

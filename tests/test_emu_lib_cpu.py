@@ -72,6 +72,13 @@ def test_differential_fuzzing(emu_lib, scenario):
     print(_run(emu_lib, scenario))
 
 
+def test_edge_cases_and_misuse(emu_lib):
+    """k = 0, ef beyond shared memory, empty batches, out-of-range ids, duplicate updates, corrupt CSR (this found a crash:
+    a decreasing row_ptr pair wrapped into an absurd stride in cozo_gpu_hnsw_stage), wrong dtype entry points, empty graphs,
+    self loops, communicator misuse: an error code or a result, never a crash"""
+    print(_run(emu_lib, "misuse"))
+
+
 def test_sanitizer_workload(emu_lib):
     """tools/sanitize.py (every kernel on tiny inputs, option sweeps on one staged graph) runs to the end: this is the run
     that exposed the stale blocking state of a re-staged PageRank graph"""

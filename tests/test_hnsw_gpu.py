@@ -230,6 +230,11 @@ def test_stage_rejects_bad_input(gpu, cfg1):
     with pytest.raises(gpu.CozoGpuError) as e:
         gpu.HnswIndex.stage(X, lv.node_ids, lv.row_ptr, bad_ci, lv.entry, m_max0=32, m_max=16)
     assert e.value.code == gpu.E_INVAL
+    bad_rp = [r.copy() for r in lv.row_ptr]
+    bad_rp[0][3] = bad_rp[0][2] - 1                      # a decreasing pair: rejected before anything is allocated
+    with pytest.raises(gpu.CozoGpuError) as e:
+        gpu.HnswIndex.stage(X, lv.node_ids, bad_rp, lv.col_idx, lv.entry, m_max0=32, m_max=16)
+    assert e.value.code == gpu.E_INVAL
 
 
 def test_device_builder_parity_and_quality(gpu):
