@@ -794,11 +794,64 @@ def scenario_misuse():
     step("every misuse answered with an error code, every edge case served")
 
 
+def scenario_fuzz_csr():
+    """staging of ARBITRARY layered CSRs (not built by this library: degrees above m_max0, empty rows, sparse upper layers,
+    unsorted rows): search results and traversal counters == oracle on the same structure, export returns the same rows in
+    key order"""
+    N, fails = FUZZ_N, 0
+    for case in range(N):
+        rng = np.random.default_rng(88000 + case)
+        n = int(rng.integers(1, 100)); dim = int(rng.choice([2, 7, 16, 40])); metric = int(rng.integers(0, 3))
+        X = rng.random((n, dim), dtype=np.float32) - 0.5 + (0.01 if metric == 1 else 0)
+        nl = int(rng.integers(1, 5))
+        node_ids, row_ptr, col_idx = [], [], []
+        members = np.arange(n)
+        for L in range(nl):
+            if L > 0:
+                keep = rng.random(len(members)) < 0.4
+                if not keep.any(): keep[rng.integers(0, len(members))] = True
+                members = members[keep]
+            rp, ci = [0], []
+            for v in members:
+                others = members[members != v]
+                deg = int(rng.integers(0, min(len(others), 45) + 1)) if rng.random() < 0.9 else 0
+                nb = rng.choice(others, size=deg, replace=False) if deg else np.zeros(0, np.int64)
+                ci += [int(x) for x in nb]; rp.append(len(ci))
+            node_ids.append(members.astype(np.uint32) if L > 0 else np.arange(n, dtype=np.uint32))
+            row_ptr.append(np.array(rp, np.uint32)); col_idx.append(np.array(ci, np.uint32))
+        entry = int(members.min())
+        desc = dict(case=case, n=n, dim=dim, metric=metric, nl=nl)
+        try:
+            g = capi.HnswIndex.stage(X, node_ids, row_ptr, col_idx, entry, metric=metric, m_max0=8, m_max=4)
+            ix = O.OracleHnsw.from_levels(X, O.HnswLevels(node_ids, row_ptr, col_idx, entry), metric=metric)
+            B = int(rng.integers(1, 10)); k = int(rng.integers(1, 12)); ef = int(rng.integers(1, 40)); mode = int(rng.choice([-1, 0, 1, 2]))
+            Q = rng.random((B, dim), dtype=np.float32) - 0.5
+            capi.set_option("hnsw.mode", mode)
+            gi, gd, gc, st = g.search(Q, k, ef)
+            capi.set_option("hnsw.mode", -1)
+            oi, od, oc, ost = ix.search(Q, k, ef, n_threads=1)
+            assert np.array_equal(gc, oc), ('count', gc, oc)
+            assert np.allclose(gd, od, rtol=1e-5, atol=1e-6, equal_nan=True), 'dist'
+            assert st.dist_evals == int(ost[:, 0].sum()), ('evals', st.dist_evals, int(ost[:, 0].sum()))
+            ni2, rp2, ci2, ep2 = g.export_levels()
+            for L in range(nl):      # rows come back in key order (ascending neighbour id), as the index relation stores them
+                assert np.array_equal(rp2[L], row_ptr[L]), 'export row_ptr'
+                for r in range(len(row_ptr[L]) - 1):
+                    a, b = int(row_ptr[L][r]), int(row_ptr[L][r + 1])
+                    assert np.array_equal(ci2[L][a:b], np.sort(col_idx[L][a:b])), 'export row'
+            assert ep2 == entry
+        except Exception as e:
+            fails += 1; print('FAIL', desc, repr(e)[:300], flush=True)
+    
+    assert fails == 0, fails
+    step(f"{N} random layered CSRs: 0 failures")
+
+
 SCENARIOS = {"graph": scenario_graph, "pagerank": scenario_pagerank, "hnsw": scenario_hnsw,
              "hnsw_maintenance": scenario_hnsw_maintenance, "builder_fidelity": scenario_builder_fidelity,
              "sharded": scenario_sharded, "fuzz_hnsw": scenario_fuzz_hnsw, "fuzz_graph": scenario_fuzz_graph,
              "fuzz_maintenance": scenario_fuzz_maintenance, "sanitize_workload": scenario_sanitize_workload,
-             "fuzz_sequences": scenario_fuzz_sequences, "fuzz_sharded": scenario_fuzz_sharded, "misuse": scenario_misuse}
+             "fuzz_sequences": scenario_fuzz_sequences, "fuzz_sharded": scenario_fuzz_sharded, "misuse": scenario_misuse, "fuzz_csr": scenario_fuzz_csr}
 
 if __name__ == "__main__":
     capi.init(0)

@@ -66,7 +66,7 @@ def test_library_scenario(emu_lib, scenario, sm_count):
     print(out)
 
 
-@pytest.mark.parametrize("scenario", ["fuzz_hnsw", "fuzz_graph", "fuzz_maintenance", "fuzz_sequences", "fuzz_sharded"])
+@pytest.mark.parametrize("scenario", ["fuzz_hnsw", "fuzz_graph", "fuzz_maintenance", "fuzz_sequences", "fuzz_sharded", "fuzz_csr"])
 def test_differential_fuzzing(emu_lib, scenario):
     """random configurations against the oracle (COZO_EMU_FUZZ=<n> cases per family, default 40; 150 + 120 + 80 + 60 + 40 were run clean)"""
     print(_run(emu_lib, scenario))
