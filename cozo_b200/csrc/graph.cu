@@ -78,6 +78,7 @@ static cudaError_t launch_sssp(cozo_gpu_graph_t* g, const uint32_t* d_sources, u
   const DeviceInfo& di = device_info();
   const size_t fstride = sssp_flags_stride(n);
   if (get_option("sssp.wide", 0) == 1) {
+    if (n_src > 65535u) return cudaErrorInvalidValue;  // sources ride on gridDim.y; the wide form is meant for a handful
     uint32_t* counts = nullptr;
     cudaError_t e = cudaMalloc(&counts, (size_t)2 * n_src * 4);
     if (e != cudaSuccess) return e;

@@ -147,8 +147,8 @@ inline void launch_dyn(G grid, B block, size_t smem, Body body, const char* name
     return;
   }
   const emu_dim3 g(grid);
-  if (g.x == 0 || g.y == 0) {
-    t_last_error = cudaErrorInvalidValue;  // a zero-sized grid is a launch error on the device too
+  if (g.x == 0 || g.y == 0 || g.z == 0 || g.x > 2147483647u || g.y > 65535u || g.z > 65535u) {
+    t_last_error = cudaErrorInvalidValue;  // a zero-sized or over-sized grid is a launch error on the device too
     return;
   }
   void* buf = nullptr;
